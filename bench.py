@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""Benchmark of the cpic hot path (BASELINE.json: particle-steps/s of the full step
+push+deposit+gather+solve, and the fraction of the HBM roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload A|B|C]
+
+N = 1 runs BASELINE.json configs[1]: conf/2d-2species.conf (the reference's two-species
+block on a 1024x1024 grid, 1e7 particles), started from the reference's own initial
+conditions. N > 1 (torchrun, one rank per GPU) is the same per-GPU workload on Y slabs
+(weak scaling: global grid 1024 x 1024*N, 1e7*N particles, device initialiser).
+A "step" is one sim_step (reference src/sim.c:481-581).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "particle-steps/sec (push+deposit+gather+solve)"
+UNIT = "particle-steps/s"
+# Algorithmic bytes per particle-step (SURVEY 8d / DESIGN.md): the fused gather+push kernel reads
+# x,y,ux,uy,uz and writes them back: 80 B; the deposit reads x,y: 16 B.
+BYTES_GATHER_PUSH = 80.0
+BYTES_DEPOSIT = 16.0
+
+WORKLOADS = {
+    # name: (conf, nx, ny per GPU, particles per species per GPU)
+    "A": ("2d-2species.conf", 1024, 1024, 5_000_000),
+    "B": ("2d-2species.conf", 2048, 2048, 50_000_000),
+    "C": ("2d-2species.conf", 4096, 4096, 500_000_000),
+}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- reference arm
+
+def scaled_conf(conf, nparticles, tmpdir="/tmp"):
+    """A copy of `conf` with `particles = nparticles` per species (bounded CPU sample)."""
+    import re
+    text = open(conf).read()
+    text = re.sub(r"particles\s*=\s*\d+", f"particles = {nparticles}", text)
+    path = os.path.join(tmpdir, f"cpic_b200_bench_{os.getpid()}.conf")
+    with open(path, "w") as f:
+        f.write(text)
+    return path
+
+
+def cpu_reference(conf, steps, warmup, budget_s=150.0):
+    """Times the reference's own CPU implementation of the path: oracle/_ref (the unmodified
+    reference sources behind single-rank shims, gcc -O3 AVX2; OmpSs-2 pragmas are inert, so it
+    runs on one core), else the oracle port. Returns (value, info)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from cpic_b200 import load_conf, init_particles
+    params, run = load_conf(conf)
+    n_full = sum(run.nparticles)
+    # bound the sample: ~1.5e7 particle-steps/s on one core is typical
+    max_n = int(budget_s * 1.5e7 / max(1, steps + warmup))
+    per_species = run.nparticles[0]
+    if n_full > max_n:
+        per_species = max(1000, max_n // len(run.nparticles))
+    sample_conf = conf if per_species == run.nparticles[0] else scaled_conf(conf, per_species)
+    n = per_species * len(run.nparticles)
+    from _refbind import RefSim, ref_available
+    if ref_available("ref"):
+        kind = "reference"
+        sim = RefSim(sample_conf, "ref")
+        step = sim.step
+    else:
+        kind = "port"
+        from _parity import oracle_from
+        p2, _ = load_conf(sample_conf)
+        sim = oracle_from(p2, init_particles(sample_conf))
+        sim.pre_step()
+        step = sim.step
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = n * steps / dt
+    info = {"value": value, "unit": UNIT, "cores": 1, "kind": kind,
+            "sample": f"{os.path.basename(conf)}: {params.nx}x{params.ny} grid, {n} particles "
+                      f"({'full workload' if n == n_full else f'{n}/{n_full} of the workload'}), {steps} steps after "
+                      f"{warmup} warm-up; serial (OmpSs-2 tasks inert), shim FFT",
+            "ms_per_step": dt / steps * 1e3}
+    return value, info
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    name, nx, ny, nps = WORKLOADS[args.workload]
+    conf = os.path.join(ROOT, "conf", name)
+    steps = min(args.steps, 20)
+    warmup = min(args.warmup, 2)
+    value, info = cpu_reference(conf, steps, warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": warmup, "ms_per_step": info["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{name} ({nx}x{ny}, {2 * nps} particles)", "host": "CPU, 1 core"},
+            "cpu_baseline": {k: info[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------- our arm
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="cpic_b200")
+    ap.add_argument("--workload", default="A", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from cpic_b200 import Sim, Params, load_conf, init_particles
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    name, nx, ny, nps = WORKLOADS[args.workload]
+    conf = os.path.join(ROOT, "conf", name)
+    params, run = load_conf(conf, rank=rank, nranks=world, device=local)
+    params.nx, params.ny = nx, ny * world        # weak scaling: one nx x ny slab per GPU
+    params.Ly = params.Ly * world
+    # keep the physics of the conf: e0 scales with the particle density (plasma frequency fixed)
+    params.e0 = params.e0 * (nps / 5_000_000) / ((nx / 1024) * (ny / 1024))
+    nspecies = len(params.q)
+    n_rank = nps * nspecies
+    n_total = n_rank * world
+
+    sim = Sim(params)
+    if world == 1 and args.workload == "A":
+        # the reference's own initial conditions (glibc rand() stream, src/particle.c:23-89)
+        parts = init_particles(conf)
+        for i, p in enumerate(parts):
+            sim.set_particles(i, p["id"], p["x"], p["y"], p["ux"], p["uy"])
+        data = "synthetic (reference initialiser: uniform random positions, u~U(-v,v), seed 138)"
+    else:
+        drift = [(5.0, 0.0), (3.0, 0.0)]
+        for i in range(nspecies):
+            sim.init_uniform(i, nps, id0=rank * nps, vx=drift[i][0], vy=drift[i][1], seed=138 + i)
+        data = "synthetic (device initialiser: uniform positions per particle block, u~U(-v,v))"
+    if world > 1:
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(sim.comm_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        sim.comm_init(bytes(idt.cpu().numpy().tobytes()))
+    sim.pre_step()
+    sim.sync()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up, then the timed region: K steps, CUDA events on the simulation's stream
+    sim.run(args.warmup)
+    sim.timing(False)
+    clocks = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        clocks.start()
+    t0 = time.perf_counter()
+    ms = sim.run_timed(args.steps)
+    barrier()
+    wall = time.perf_counter() - t0
+    clk = clocks.stop() if rank == 0 else None
+    _, launches0 = sim.get_timing()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = n_total * args.steps / (ms * 1e-3)
+
+    # ---- per-stage device time over another K steps (events around every stage; separate pass
+    # because the per-stage synchronisation perturbs the whole-step timing above)
+    sim.timing(True)
+    sim.run(args.steps)
+    stage_ms, launches = sim.get_timing()
+    sim.timing(False)
+    peak, peak_src = measured_peak()
+    k_launches = args.steps * nspecies
+    t_push = stage_ms["gather_push"] / k_launches          # ms per k_gather_push launch
+    achieved = BYTES_GATHER_PUSH * nps / (t_push * 1e-3) / 1e9 if t_push > 0 else 0.0
+    t_dep = stage_ms["field_rho"] / args.steps
+    roofline = {"bound": "hbm", "kernel": "k_gather_push<2> (fused field gather + Boris push)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "peak_source": peak_src, "traffic": None,
+                "algorithmic_bytes_per_particle": BYTES_GATHER_PUSH, "particles_per_launch": nps,
+                "avg_launch_ms": t_push,
+                "whole_step_frac": (n_rank * args.steps / (ms * 1e-3)) * (BYTES_GATHER_PUSH + BYTES_DEPOSIT) / 1e9 / peak,
+                "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()}}
+
+    # ---- e2e: the same K steps with the particle state living in pinned HOST memory: every step
+    # uploads it, runs one sim_step through the C ABI, and reads back particles and the four grids
+    e2e = None
+    if not args.no_e2e:
+        import ctypes as C
+        L = sim.L
+        nbytes = L.cpic_b200_image_bytes(sim.h)
+        host = L.cpic_b200_host_alloc(nbytes)
+        fields = {k: np.empty(sim.field_shape(k)) for k in ("rho", "phi", "Ex", "Ey")}
+        fbytes = sum(a.nbytes for a in fields.values())
+        assert host, "pinned allocation failed"
+        L.cpic_b200_image_download(sim.h, host, nbytes)
+        e_steps = max(3, min(args.steps, 10))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            L.cpic_b200_image_upload(sim.h, host, nbytes)
+            sim.step()
+            L.cpic_b200_image_download(sim.h, host, nbytes)
+            for k, a in fields.items():
+                L.cpic_b200_get_field(sim.h, {"rho": 0, "phi": 1, "Ex": 2, "Ey": 3}[k], a.ctypes.data_as(C.c_void_p))
+        sim.sync()
+        barrier()
+        te = time.perf_counter() - t0
+        te_t = torch.tensor([te], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(te_t, op=dist.ReduceOp.MAX)
+        te = float(te_t.item())
+        L.cpic_b200_host_free(host)
+        e2e = {"value": n_total * e_steps / te, "unit": UNIT, "h2d_bytes_per_step": int(nbytes),
+               "d2h_bytes_per_step": int(nbytes + fbytes), "steps": e_steps,
+               "note": "particle state round-trips through pinned host memory every step (worst case of the "
+                       "drop-in: host-owned plist); resident mode only reads the grids back"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        _, cpu = cpu_reference(conf, 3, 1, budget_s=30.0)
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": data,
+                "config": {"workload": f"{name}: {nx}x{ny} grid and {n_rank} particles per GPU "
+                                       f"({params.nx}x{params.ny}, {n_total} particles in total), 2 species, "
+                                       f"B=(0,0,-0.2), dt=5e-3",
+                           "parallelism": f"{world} Y-slab(s), one per GPU",
+                           "l2": "particle state per GPU (%.0f MB) exceeds the 126 MB L2" % (n_rank * 48 / 1e6)},
+                "clocks": clk, "e2e": e2e, "gpu_launches": int(launches0),
+                "roofline": roofline, "cpu_baseline": cpu, "wall_s_timed_region": wall}
+        print(json.dumps(line))
+    sim.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,32 @@
+/* Multi-GPU layer of cpic_b200: one Y slab per rank, NCCL over NVLink.
+ * Replaces the reference's MPI traffic: rho ghost row (src/comm_field.c:51-136), phi
+ * ghost rows (:139-201), particles crossing a slab face (src/comm_plasma.c:887-1120)
+ * and FFTW-MPI's transposes inside the MFT solver (src/solver.c:314-330, :485-491). */
+#ifndef CPIC_B200_COMM_H
+#define CPIC_B200_COMM_H
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+#include "geom.h"
+
+struct SpeciesDev;
+struct Comm;
+
+int comm_unique_id(void *id128, char *err, size_t errlen);
+Comm *comm_create(const void *id128, int rank, int nranks, const Geom &g, cudaStream_t stream,
+		char *err, size_t errlen);
+void comm_destroy(Comm *c);
+
+/* rho: ghost row ny -> rank+1, received row added to row 0 */
+int comm_rho_halo(Comm *c, double *rho, cudaStream_t stream, long long *launches);
+/* phi: slab rows 0,1 -> rank-1's south ghosts; slab row ny-1 -> rank+1's north ghost */
+int comm_phi_halo(Comm *c, double *phi, cudaStream_t stream);
+/* particles: outbox entries of the edge block rows that leave the slab are sent to the
+ * neighbour ranks and land in the ghost outbox rows nb .. nb+2*nbx */
+int comm_particles(Comm *c, SpeciesDev *sp, const Geom &g, int nb, cudaStream_t stream,
+		int *errflag, long long *launches);
+/* distributed MFT solve: rho slab rows -> unnormalised phi slab rows (ny x S) */
+int comm_solve(Comm *c, const double *rho, double *phi_raw, cudaStream_t stream, long long *launches);
+
+#endif

@@ -1,0 +1,133 @@
+/* Geometry and per-particle arithmetic shared by the host binning code and the device
+ * kernels, so that both place a particle in exactly the same cell. */
+#ifndef CPIC_B200_GEOM_H
+#define CPIC_B200_GEOM_H
+
+#include <math.h>
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define HD __host__ __device__ __forceinline__
+#else
+#define HD static inline
+#endif
+
+/* Every floating point operation of the per-particle arithmetic is pinned (no compiler
+ * contraction), so that the separately staged kernels and the fused ones, and the host
+ * binning code, produce identical bits. */
+#ifdef __CUDA_ARCH__
+#define MUL(a, b) __dmul_rn((a), (b))
+#define ADD(a, b) __dadd_rn((a), (b))
+#define SUB(a, b) __dsub_rn((a), (b))
+#define FMA(a, b, c) __fma_rn((a), (b), (c))
+#else
+#define MUL(a, b) ((a) * (b))
+#define ADD(a, b) ((a) + (b))
+#define SUB(a, b) ((a) - (b))
+#define FMA(a, b, c) fma((a), (b), (c))
+#endif
+
+/* Destination codes of a particle that leaves its particle block: (ddy+1)*3 + (ddx+1)
+ * for a move to an adjacent block, 4 = stays. */
+#define DEST_STAY 4
+#define DEST_FAR 9
+
+/* Deferred error bits (device flag word) */
+#define ERRBIT_VELOCITY 1
+#define ERRBIT_CAPACITY 2
+#define ERRBIT_FAR 4
+#define ERRBIT_TMA 8
+
+/* One rank's slab and its decomposition into particle blocks of BX x BY cells */
+struct Geom {
+	int nx, ny;          /* grid points of the slab: all columns, ny = ny_glob / nranks rows */
+	int ny_glob;
+	int row0;            /* first global row of the slab = rank * ny */
+	int S;               /* row stride of rho and phi: 2*(nx/2+1) (reference src/solver.c:381-433) */
+	int SE;              /* row stride of the device E arrays: nx + wrap columns, even */
+	int BX, BY;          /* cells per particle block */
+	int nbx, nby;        /* blocks per slab row / column */
+	int nby_glob;        /* nby * nranks */
+	int brow0;           /* first global block row = rank * nby */
+	int WPC;             /* particle blocks (warps) per CTA, divides nbx */
+	int TW, TH;          /* E tile: TW = WPC*BX + 2 columns (even), TH = BY + 1 rows */
+	int tile_dbl;        /* doubles between the E_x and E_y tiles in shared memory (128 B multiple) */
+	double Lx, Ly;       /* global lengths */
+	double dx, dy;       /* reference src/sim.c:172-176 */
+	double idx, idy;     /* 1.0 / dx, as the reference forms them (src/interpolate.c:300-303) */
+	double y0;           /* slab origin: field.x0[Y] = rank * ny * dy (src/field.c:149-151) */
+};
+
+/* Cell of a position, the reference's way (src/interpolate.c:38-66: block_delta * idx,
+ * floor), clamped into the slab so that a particle sitting exactly on the upper edge
+ * (x == L after a wrap from -eps, src/comm_plasma.c:738-742) stays addressable.
+ * Returns the clamped floor as a double (needed for the in-cell offset). */
+HD double
+cell_floor_x(const Geom &g, double x)
+{
+	double bs = floor(MUL(x, g.idx));
+	return fmin(fmax(bs, 0.0), (double) (g.nx - 1));
+}
+
+HD double
+cell_floor_y(const Geom &g, double y)
+{
+	double bs = floor(MUL(SUB(y, g.y0), g.idy));
+	return fmin(fmax(bs, 0.0), (double) (g.ny - 1));
+}
+
+/* Global row of a position (for the exchange between slabs) */
+HD int
+global_row(const Geom &g, double y)
+{
+	double bs = floor(MUL(y, g.idy));
+	return (int) fmin(fmax(bs, 0.0), (double) (g.ny_glob - 1));
+}
+
+/* Bilinear (CIC) weights, restating reference src/interpolate.c:77-100 (weights),
+ * :38-66 (relative_position_grid) and :11-32 (linear_interpolation). The Y offset uses
+ * dx[X] as the reference does (src/interpolate.c:87-88). */
+HD void
+cic_weights(const Geom &g, double x, double y, int &i0x, int &i0y,
+		double &w00, double &w01, double &w10, double &w11)
+{
+	double bd, bs, relx, rely, delx, dely;
+
+	bd = x;
+	bs = cell_floor_x(g, x);
+	i0x = (int) bs;
+	relx = MUL(SUB(bd, MUL(bs, g.dx)), g.idx);
+
+	bd = SUB(y, g.y0);
+	bs = cell_floor_y(g, y);
+	i0y = (int) bs;
+	rely = MUL(SUB(bd, MUL(bs, g.dx)), g.idy);
+
+	delx = SUB(1.0, relx);
+	dely = SUB(1.0, rely);
+	w00 = MUL(delx, dely);
+	w01 = MUL(delx, rely);
+	w10 = MUL(relx, dely);
+	w11 = MUL(relx, rely);
+}
+
+/* Local particle block of a position inside the slab */
+HD int
+block_of(const Geom &g, double x, double y)
+{
+	int cx = (int) cell_floor_x(g, x);
+	int cy = (int) cell_floor_y(g, y);
+	return (cy / g.BY) * g.nbx + cx / g.BX;
+}
+
+/* Shortest signed distance between two indices on a ring of n */
+HD int
+ring_delta(int to, int from, int n)
+{
+	int d = to - from;
+	if(2 * d > n) d -= n;
+	else if(2 * d < -n) d += n;
+	return d;
+}
+
+#endif

@@ -1,0 +1,688 @@
+/* Device kernels of the cpic_b200 hot path (sm_100a).
+ *
+ * Particle storage ("particle blocks"): every species is a set of fixed-capacity SoA
+ * segments, one per block of BX x BY grid cells; segment b holds exactly the particles
+ * whose cell lies in block b, in a deterministic order. One warp owns one particle
+ * block for the duration of a kernel and walks it sequentially in batches of 32, so
+ * every running count, compaction and floating point sum inside a block has a fixed
+ * order; blocks only meet through fixed-order reads of neighbour outboxes / halo
+ * arrays. No floating point atomics are used anywhere.
+ */
+#ifndef CPIC_B200_KERNELS_CUH
+#define CPIC_B200_KERNELS_CUH
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cufft.h>
+#include <stdint.h>
+
+#include "geom.h"
+
+#define FULL 0xffffffffu
+#define MAX_WPC 8
+
+/* Device view of one species */
+struct SpeciesDev {
+	double *x, *y, *ux, *uy, *uz;
+	double *pEx, *pEy;       /* gathered field per particle, optional (may be NULL) */
+	long long *id;
+	int *count;              /* particles per block */
+	/* outbox: particles that left the block in the last push, in block order */
+	double *ox, *oy, *oux, *ouy, *ouz;
+	double *oEx, *oEy;       /* travel with the particle when pEx is kept (ppack.E, reference src/def.h:96) */
+	long long *oid;
+	int *odest;              /* destination code (geom.h) */
+	int *ohole;              /* slot the particle vacated */
+	int *ocount;
+	int cap, ocap;
+};
+
+/* Everything the mover needs besides the particle (reference src/mover.c:191-226) */
+struct PushParams {
+	double dt;               /* -dt/2 at iteration 0 */
+	double dtqm2;            /* 0.5 * dt * q / m */
+	double tx, ty, tz;       /* t = B * dtqm2 (reference src/mover.c:45) */
+	double sx, sy, sz;       /* s = 2t / (1 + t^2), per component (src/mover.c:46,51) */
+	double umax_x, umax_y, umax_z;
+	int set_r;               /* 0 at iteration 0: velocities only */
+};
+
+/* ------------------------------------------------------------------------ TMA */
+
+__device__ __forceinline__ uint32_t
+smem_u32(const void *p)
+{
+	return (uint32_t) __cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void
+mbar_init(uint64_t *bar, int count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void
+mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+			:: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+/* Returns 0 on success, 1 when the barrier did not complete (descriptor error): the
+ * caller raises an error flag instead of hanging the device. */
+__device__ __forceinline__ int
+mbar_wait(uint64_t *bar, uint32_t parity)
+{
+	uint32_t done = 0;
+	for(int spin = 0; spin < (1 << 22); spin++)
+	{
+		asm volatile("{\n\t.reg .pred p;\n\t"
+				"mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+				"selp.u32 %0, 1, 0, p;\n\t}"
+				: "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+		if(done) return 0;
+	}
+	return 1;
+}
+
+/* 2D tile load: box (TW x TH doubles) of a row-major array whose first coordinate is
+ * the column. Out-of-range elements are zero-filled by the TMA unit. */
+__device__ __forceinline__ void
+tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar)
+{
+	asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+			" [%0], [%1, {%2, %3}], [%4];"
+			:: "r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+			: "memory");
+}
+
+/* ------------------------------------------------------------ field kernels */
+
+/* MFT_kernel, reference src/solver.c:337-363: g[l][k] *= G[l][k]. 16 B per element
+ * read + 8 B of G + 16 B written: HBM-bound streaming. */
+__global__ void
+k_green(cufftDoubleComplex *__restrict__ g, const double *__restrict__ G, size_t n)
+{
+	size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+	size_t stride = (size_t) gridDim.x * blockDim.x;
+	for(; i < n; i += stride)
+	{
+		cufftDoubleComplex v = g[i];
+		double c = G[i];
+		v.x *= c;
+		v.y *= c;
+		g[i] = v;
+	}
+}
+
+/* MFT_normalize (reference src/solver.c:365-379: phi /= nx*ny on the nx live columns)
+ * fused with the single-rank phi halo (src/comm_field.c:139-201: slab rows 0,1 become
+ * the south ghosts, row ny-1 the north ghost). `raw` is the Z2D output (ny x S), `phi`
+ * the ny+3 row array. With several ranks only the slab rows are written here and the
+ * ghosts arrive over NCCL. */
+__global__ void
+k_phi_finish(const double *__restrict__ raw, double *__restrict__ phi, Geom g, double N,
+		int fill_ghosts)
+{
+	int c = blockIdx.x * blockDim.x + threadIdx.x;
+	int r = blockIdx.y;               /* row of the ny+3 row array */
+	int src;
+	if(c >= g.S) return;
+	if(r >= 1 && r <= g.ny) src = r - 1;
+	else if(!fill_ghosts) return;
+	else if(r == 0) src = g.ny - 1;
+	else src = r - 1 - g.ny;          /* rows ny+1, ny+2 <- slab rows 0, 1 */
+	double v = raw[(size_t) src * g.S + c];
+	if(c < g.nx) v /= N;
+	phi[(size_t) r * g.S + c] = v;
+}
+
+/* field_E_compute, reference src/field.c:358-416: centred differences of phi on rows
+ * [0, ny], X periodic, Y through the ghost rows. Also fills the wrap columns
+ * [nx, SE) of the device E arrays (column nx+j repeats column j) so that a particle
+ * block at the right edge can fetch its tile with one TMA box. */
+__global__ void
+k_field_E(const double *__restrict__ phi, double *__restrict__ Ex, double *__restrict__ Ey,
+		Geom g)
+{
+	int ix = blockIdx.x * blockDim.x + threadIdx.x;
+	int iy = blockIdx.y;              /* 0 .. ny */
+	if(ix >= g.SE) return;
+	int c = ix % g.nx;
+	int x0 = c == 0 ? g.nx - 1 : c - 1;
+	int x1 = c == g.nx - 1 ? 0 : c + 1;
+	const double *p = phi + (size_t) (iy + 1) * g.S;   /* slab row iy is array row iy+1 */
+	double dx2 = 2 * g.dx, dy2 = 2 * g.dy;
+	Ey[(size_t) iy * g.SE + ix] = (p[c - g.S] - p[c + g.S]) / dy2;
+	Ex[(size_t) iy * g.SE + ix] = (p[x0] - p[x1]) / dx2;
+}
+
+/* Second half of the deposition: adds, in a fixed order, the halo sums that the CTAs of
+ * k_deposit left in hb (bottom rows), hr (right columns) and hc (corners) to the nodes
+ * they belong to. Row ny (the south ghost row of `_rho`) is owned by nobody and is
+ * assembled here from scratch. Grid: (ceil(nx/128), nby) -- rows y = (by+1)*BY. */
+__global__ void
+k_stitch_rows(double *__restrict__ rho, const double *__restrict__ hb,
+		const double *__restrict__ hr, const double *__restrict__ hc, Geom g)
+{
+	int x = blockIdx.x * blockDim.x + threadIdx.x;
+	int by = blockIdx.y + 1;          /* 1 .. nby */
+	if(x >= g.nx) return;
+	int y = by * g.BY;
+	int W = g.WPC * g.BX, ncx = g.nbx / g.WPC;
+	double v = y < g.ny ? rho[(size_t) y * g.S + x] : 0.0;
+	v += hb[(size_t) (by - 1) * g.nx + x];
+	if(x % W == 0)
+	{
+		int left = (x / W + ncx - 1) % ncx;
+		if(y < g.ny) v += hr[(size_t) left * g.ny + y];
+		v += hc[(size_t) (by - 1) * ncx + left];
+	}
+	rho[(size_t) y * g.S + x] = v;
+}
+
+/* Right-column halos for the rows k_stitch_rows does not visit. Grid: (ceil(ny/128), ncx) */
+__global__ void
+k_stitch_cols(double *__restrict__ rho, const double *__restrict__ hr, Geom g)
+{
+	int y = blockIdx.x * blockDim.x + threadIdx.x;
+	int cx = blockIdx.y;
+	if(y >= g.ny) return;
+	if(y % g.BY == 0 && y > 0) return;
+	int W = g.WPC * g.BX, ncx = g.nbx / g.WPC;
+	int left = (cx + ncx - 1) % ncx;
+	rho[(size_t) y * g.S + (size_t) cx * W] += hr[(size_t) left * g.ny + y];
+}
+
+/* Single rank: the ghost row goes to ourselves and is added to row 0
+ * (reference src/comm_field.c:51-136). With several ranks `recv` is the row received
+ * from rank-1. */
+__global__ void
+k_rho_fold(double *__restrict__ rho, const double *__restrict__ recv, Geom g)
+{
+	int x = blockIdx.x * blockDim.x + threadIdx.x;
+	if(x >= g.nx) return;
+	rho[x] += recv[x];
+}
+
+/* ---------------------------------------------------------- particle kernels */
+
+/* Shared memory carve-up of the particle kernels (dynamic):
+ *   [0, 16)                      mbarrier
+ *   [128, 128 + 2*TH*TW*8)       E_x tile, E_y tile (TMA destinations, 128 B aligned)
+ * The deposit kernel uses WPC*(BY+1)*(BX+1) doubles instead. */
+
+__device__ __forceinline__ void
+boris(const PushParams &pp, double Ex, double Ey, double &ux, double &uy, double &uz)
+{
+	/* reference src/mover.c:22-70; per-component s denominator as in the reference */
+	const double k = pp.dtqm2;
+	/* t and s depend on the species only (B is uniform): formed once on the host */
+	const double tx = pp.tx, ty = pp.ty, tz = pp.tz, sx = pp.sx, sy = pp.sy, sz = pp.sz;
+	const double mx = FMA(k, Ex, ux), my = FMA(k, Ey, uy), mz = uz;      /* E_z = 0 */
+	const double px = ADD(SUB(MUL(my, tz), MUL(mz, ty)), mx);
+	const double py = ADD(SUB(MUL(mz, tx), MUL(mx, tz)), my);
+	const double pz = ADD(SUB(MUL(mx, ty), MUL(my, tx)), mz);
+	const double qx = ADD(SUB(MUL(py, sz), MUL(pz, sy)), mx);
+	const double qy = ADD(SUB(MUL(pz, sx), MUL(px, sz)), my);
+	const double qz = ADD(SUB(MUL(px, sy), MUL(py, sx)), mz);
+	ux = FMA(k, Ex, qx);
+	uy = FMA(k, Ey, qy);
+	uz = qz;
+}
+
+/* Bilinear gather from the CTA's E tile (reference src/interpolate.c:102-155). lx, ly
+ * are the cell's coordinates inside the tile. */
+__device__ __forceinline__ double
+tile_gather(const double *t, int TW, int lx, int ly, double w00, double w01, double w10, double w11)
+{
+	const double *p = t + ly * TW + lx;
+	double v = MUL(w00, p[0]);
+	v = FMA(w01, p[TW], v);
+	v = FMA(w10, p[1], v);
+	v = FMA(w11, p[TW + 1], v);
+	return v;
+}
+
+/* MODE 0: stage_plasma_E alone   (gather, store E per particle)
+ * MODE 1: stage_plasma_r alone   (push from the stored per-particle E)
+ * MODE 2: both fused             (gather + push; E kept per particle when pEx != NULL)
+ *
+ * One warp per particle block, WPC blocks of one block row per CTA sharing one E tile
+ * fetched by TMA. After the push a particle whose cell left the block is appended to
+ * the block's outbox (with the slot it vacated) and its slot is poisoned with NaN; the
+ * others are written back in place. */
+template <int MODE>
+__global__ void __launch_bounds__(32 * MAX_WPC)
+k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
+		const __grid_constant__ CUtensorMap mapEx, const __grid_constant__ CUtensorMap mapEy,
+		int *__restrict__ errflag)
+{
+	extern __shared__ __align__(128) unsigned char smem[];
+	uint64_t *bar = (uint64_t *) smem;
+	double *tEx = (double *) (smem + 128);
+	double *tEy = tEx + g.tile_dbl;
+
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int ncx = g.nbx / g.WPC;
+	const int by = blockIdx.x / ncx, cx = blockIdx.x % ncx;
+	const int bx = cx * g.WPC + warp;
+	const int b = by * g.nbx + bx;
+
+	if(MODE != 1)
+	{
+		if(threadIdx.x == 0)
+		{
+			mbar_init(bar, 1);
+			uint32_t bytes = 2u * (uint32_t) (g.TH * g.TW) * 8u;
+			mbar_expect_tx(bar, bytes);
+			tma_load_2d(tEx, &mapEx, cx * g.WPC * g.BX, by * g.BY, bar);
+			tma_load_2d(tEy, &mapEy, cx * g.WPC * g.BX, by * g.BY, bar);
+		}
+		__syncthreads();
+		if(mbar_wait(bar, 0))
+		{
+			if(threadIdx.x == 0) atomicOr(errflag, ERRBIT_TMA);
+			return;
+		}
+	}
+
+	const int cnt = sp.count[b];
+	const size_t base = (size_t) b * sp.cap;
+	const size_t obase = (size_t) b * sp.ocap;
+	const int tx0 = cx * g.WPC * g.BX, ty0 = by * g.BY;   /* tile origin in cells */
+	const int gby = g.brow0 + by;
+	int nout = 0;
+	int bad = 0;
+
+	for(int i0 = 0; i0 < cnt; i0 += 32)
+	{
+		const int i = i0 + lane;
+		const bool valid = i < cnt;
+		const size_t s = base + (valid ? i : 0);
+		double x = 0, y = 0, ux = 0, uy = 0, uz = 0, Ex = 0, Ey = 0;
+
+		if(valid)
+		{
+			x = sp.x[s]; y = sp.y[s];
+			if(MODE != 0) { ux = sp.ux[s]; uy = sp.uy[s]; uz = sp.uz[s]; }
+			if(MODE == 1) { Ex = sp.pEx[s]; Ey = sp.pEy[s]; }
+		}
+
+		if(MODE != 1 && valid)
+		{
+			int i0x, i0y;
+			double w00, w01, w10, w11;
+			cic_weights(g, x, y, i0x, i0y, w00, w01, w10, w11);
+			Ex = tile_gather(tEx, g.TW, i0x - tx0, i0y - ty0, w00, w01, w10, w11);
+			Ey = tile_gather(tEy, g.TW, i0x - tx0, i0y - ty0, w00, w01, w10, w11);
+			if(MODE == 0 || sp.pEx) { sp.pEx[s] = Ex; sp.pEy[s] = Ey; }
+		}
+
+		if(MODE == 0) continue;
+
+		int dest = DEST_STAY;
+		if(valid)
+		{
+			boris(pp, Ex, Ey, ux, uy, uz);
+			/* reference src/mover.c:97-137 aborts; here the flag is raised and the
+			 * host reports it at the next synchronisation */
+			if(fabs(ux) > pp.umax_x || fabs(uy) > pp.umax_y || fabs(uz) > pp.umax_z) bad = 1;
+
+			if(pp.set_r)
+			{
+				x = FMA(ux, pp.dt, x);
+				y = FMA(uy, pp.dt, y);
+				/* periodic_boundary_ppack, reference src/comm_plasma.c:725-747 */
+				if(x >= g.Lx) x = SUB(x, g.Lx); else if(x < 0.0) x = ADD(x, g.Lx);
+				if(y >= g.Ly) y = SUB(y, g.Ly); else if(y < 0.0) y = ADD(y, g.Ly);
+
+				int ncxb = (int) cell_floor_x(g, x) / g.BX;
+				int ngby = global_row(g, y) / g.BY;
+				int ddx = ring_delta(ncxb, bx, g.nbx);
+				int ddy = ring_delta(ngby, gby, g.nby_glob);
+				if(ddx < -1 || ddx > 1 || ddy < -1 || ddy > 1) dest = DEST_FAR;
+				else dest = (ddy + 1) * 3 + (ddx + 1);
+			}
+		}
+
+		const bool leave = valid && dest != DEST_STAY;
+		if(valid && !leave)
+		{
+			if(pp.set_r) { sp.x[s] = x; sp.y[s] = y; }
+			sp.ux[s] = ux; sp.uy[s] = uy; sp.uz[s] = uz;
+		}
+
+		const unsigned m = __ballot_sync(FULL, leave);
+		if(m)
+		{
+			if(leave)
+			{
+				int pos = nout + __popc(m & ((1u << lane) - 1));
+				if(dest == DEST_FAR) bad |= 4;
+				if(pos < sp.ocap)
+				{
+					size_t o = obase + pos;
+					sp.ox[o] = x; sp.oy[o] = y;
+					sp.oux[o] = ux; sp.ouy[o] = uy; sp.ouz[o] = uz;
+					sp.oid[o] = sp.id[s];
+					if(sp.oEx) { sp.oEx[o] = Ex; sp.oEy[o] = Ey; }
+					sp.odest[o] = dest;
+					sp.ohole[o] = i;
+				}
+				else bad |= 2;
+				sp.x[s] = __longlong_as_double(0x7ff8000000000000LL);   /* hole marker */
+			}
+			nout += __popc(m);
+		}
+	}
+
+	if(MODE != 0)
+	{
+		if(lane == 0) sp.ocount[b] = nout < sp.ocap ? nout : sp.ocap;
+		if(bad)
+		{
+			int bits = 0;
+			if(bad & 1) bits |= ERRBIT_VELOCITY;
+			if(bad & 2) bits |= ERRBIT_CAPACITY;
+			if(bad & 4) bits |= ERRBIT_FAR;
+			atomicOr(errflag, bits);
+		}
+	}
+}
+
+/* comm_plasma on the device (reference src/comm_plasma.c:1122-1142, X and Y passes in
+ * one): (1) the holes left by the leavers are filled with the block's last remaining
+ * particles, in order; (2) the particles that the eight neighbour blocks put in their
+ * outboxes for this block are appended, neighbours in a fixed order. With several ranks
+ * the block rows -1 and nby are ghost outboxes filled from the neighbour ranks.
+ * One warp per block; grid = nb / 8 CTAs of 8 warps (blocks need not share a row). */
+__global__ void __launch_bounds__(256)
+k_migrate(SpeciesDev sp, Geom g, int nb, int *__restrict__ errflag)
+{
+	const int lane = threadIdx.x & 31;
+	const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	if(b >= nb) return;
+
+	const int cnt = sp.count[b];
+	const int no = sp.ocount[b];
+	const size_t base = (size_t) b * sp.cap;
+	const size_t obase = (size_t) b * sp.ocap;
+	int n = cnt - no;                 /* particles that stay */
+
+	/* (1) holes below n are filled from the live slots in [n, cnt) */
+	if(no > 0)
+	{
+		int filled = 0;               /* next hole to fill = ohole[filled] (ascending) */
+		for(int i0 = n; i0 < cnt; i0 += 32)
+		{
+			const int i = i0 + lane;
+			const bool live = i < cnt && sp.x[base + i] == sp.x[base + i];
+			const unsigned m = __ballot_sync(FULL, live);
+			if(live)
+			{
+				const int k = filled + __popc(m & ((1u << lane) - 1));
+				const size_t d = base + sp.ohole[obase + k];
+				const size_t s = base + i;
+				sp.x[d] = sp.x[s]; sp.y[d] = sp.y[s];
+				sp.ux[d] = sp.ux[s]; sp.uy[d] = sp.uy[s]; sp.uz[d] = sp.uz[s];
+				sp.id[d] = sp.id[s];
+				if(sp.pEx) { sp.pEx[d] = sp.pEx[s]; sp.pEy[d] = sp.pEy[s]; }
+			}
+			filled += __popc(m);
+		}
+	}
+
+	/* (2) arrivals. Neighbour k sits at (dx, dy) = (k%3-1, k/3-1); what it sends to us
+	 * carries the opposite code 8-k. Ghost block rows hold the other ranks' particles. */
+	const int bx = b % g.nbx, by = b / g.nbx;
+	for(int k = 0; k < 9; k++)
+	{
+		if(k == DEST_STAY) continue;
+		const int ndx = k % 3 - 1, ndy = k / 3 - 1;
+		int nbx_ = bx + ndx, nby_ = by + ndy;
+		if(nbx_ < 0) nbx_ += g.nbx; else if(nbx_ >= g.nbx) nbx_ -= g.nbx;
+		int src;                       /* index into the outbox arrays */
+		if(g.nby_glob == g.nby)
+		{
+			if(nby_ < 0) nby_ += g.nby; else if(nby_ >= g.nby) nby_ -= g.nby;
+			src = nby_ * g.nbx + nbx_;
+		}
+		else if(nby_ < 0) src = nb + nbx_;                 /* north ghost row */
+		else if(nby_ >= g.nby) src = nb + g.nbx + nbx_;    /* south ghost row */
+		else src = nby_ * g.nbx + nbx_;
+
+		const int want = 8 - k;
+		const int m_ = sp.ocount[src];
+		const size_t sbase = (size_t) src * sp.ocap;
+		for(int j0 = 0; j0 < m_; j0 += 32)
+		{
+			const int j = j0 + lane;
+			const bool hit = j < m_ && sp.odest[sbase + j] == want;
+			const unsigned m = __ballot_sync(FULL, hit);
+			if(hit)
+			{
+				const int pos = n + __popc(m & ((1u << lane) - 1));
+				if(pos < sp.cap)
+				{
+					const size_t d = base + pos, s = sbase + j;
+					sp.x[d] = sp.ox[s]; sp.y[d] = sp.oy[s];
+					sp.ux[d] = sp.oux[s]; sp.uy[d] = sp.ouy[s]; sp.uz[d] = sp.ouz[s];
+					sp.id[d] = sp.oid[s];
+					if(sp.pEx) { sp.pEx[d] = sp.oEx[s]; sp.pEy[d] = sp.oEy[s]; }
+				}
+				else atomicOr(errflag, ERRBIT_CAPACITY);
+			}
+			n += __popc(m);
+		}
+	}
+	if(lane == 0) sp.count[b] = n < sp.cap ? n : sp.cap;
+}
+
+/* interpolate_p2f_rho, reference src/interpolate.c:282-346 / :161-276, accumulate-correct.
+ * Each warp sums its block's particles into a private (BY+1) x (BX+1) tile in shared
+ * memory: per batch of 32, lanes that share a cell are summed in lane order by the
+ * lowest of them (match_any + shuffles), then the four corners are added in four
+ * phases; inside a phase distinct cells hit distinct nodes, so plain read-modify-write
+ * is race free and the order of every node's sum is fixed. The CTA then merges its WPC
+ * tiles left to right and stores: interior nodes to rho (`=` for the first species,
+ * `+=` after), bottom row / right column / corner to the halo arrays that
+ * k_stitch_* add in a fixed order. rho_reset (src/field.c:163-210) is implicit. */
+template <bool FIRST>
+__global__ void __launch_bounds__(32 * MAX_WPC)
+k_deposit(SpeciesDev sp, Geom g, double vq,
+		double *__restrict__ rho, double *__restrict__ hb, double *__restrict__ hr,
+		double *__restrict__ hc)
+{
+	extern __shared__ __align__(128) unsigned char smem[];
+	double *tiles = (double *) smem;
+	const int TWd = g.BX + 1, THd = g.BY + 1, tsz = TWd * THd;
+
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int ncx = g.nbx / g.WPC;
+	const int by = blockIdx.x / ncx, cx = blockIdx.x % ncx;
+	const int bx = cx * g.WPC + warp;
+	const int b = by * g.nbx + bx;
+	double *t = tiles + warp * tsz;
+
+	for(int k = lane; k < tsz; k += 32) t[k] = 0.0;
+	__syncwarp();
+
+	const int cnt = sp.count[b];
+	const size_t base = (size_t) b * sp.cap;
+	const int cx0 = bx * g.BX, cy0 = by * g.BY;
+
+	for(int i0 = 0; i0 < cnt; i0 += 32)
+	{
+		const int i = i0 + lane;
+		const bool valid = i < cnt;
+		int cell = -1 - lane;         /* unique key for idle lanes */
+		int node = 0;
+		double a00 = 0, a01 = 0, a10 = 0, a11 = 0;
+		if(valid)
+		{
+			int i0x, i0y;
+			double w00, w01, w10, w11;
+			cic_weights(g, sp.x[base + i], sp.y[base + i], i0x, i0y, w00, w01, w10, w11);
+			a00 = MUL(w00, vq); a01 = MUL(w01, vq); a10 = MUL(w10, vq); a11 = MUL(w11, vq);
+			node = (i0y - cy0) * TWd + (i0x - cx0);
+			cell = node;
+		}
+		const unsigned peers = __match_any_sync(FULL, cell);
+		const int leader = __ffs(peers) - 1;
+		const int npeers = __popc(peers);
+		const int maxp = __reduce_max_sync(FULL, npeers);
+		/* the leader adds its peers' terms in ascending lane order */
+		for(int j = 1; j < maxp; j++)
+		{
+			int src = lane;
+			if(lane == leader && j < npeers) src = __fns(peers, 0, j + 1);
+			double b00 = __shfl_sync(FULL, a00, src);
+			double b01 = __shfl_sync(FULL, a01, src);
+			double b10 = __shfl_sync(FULL, a10, src);
+			double b11 = __shfl_sync(FULL, a11, src);
+			if(lane == leader && j < npeers) { a00 += b00; a01 += b01; a10 += b10; a11 += b11; }
+		}
+		const bool add = valid && lane == leader;
+		if(add) t[node] += a00;
+		__syncwarp();
+		if(add) t[node + TWd] += a01;
+		__syncwarp();
+		if(add) t[node + 1] += a10;
+		__syncwarp();
+		if(add) t[node + TWd + 1] += a11;
+		__syncwarp();
+	}
+
+	__syncthreads();
+
+	/* merge the WPC private tiles and store */
+	const int W = g.WPC * g.BX;
+	for(int k = threadIdx.x; k < THd * (W + 1); k += blockDim.x)
+	{
+		const int r = k / (W + 1), c = k % (W + 1);
+		const int w = c / g.BX, j = c % g.BX;
+		double v;
+		if(c == W) v = tiles[(g.WPC - 1) * tsz + r * TWd + g.BX];
+		else
+		{
+			v = tiles[w * tsz + r * TWd + j];
+			if(j == 0 && w > 0) v += tiles[(w - 1) * tsz + r * TWd + g.BX];
+		}
+		double *dst;
+		if(r < g.BY && c < W) dst = rho + (size_t) (by * g.BY + r) * g.S + (size_t) cx * W + c;
+		else if(r == g.BY && c < W) dst = hb + (size_t) by * g.nx + (size_t) cx * W + c;
+		else if(r < g.BY) dst = hr + (size_t) cx * g.ny + by * g.BY + r;
+		else dst = hc + (size_t) by * ncx + cx;
+		if(FIRST) *dst = v;
+		else *dst += v;
+	}
+}
+
+/* Kinetic energy per species: sum(ux^2 + uy^2), reference src/sim.c:366-395 (compiled
+ * out there). One warp per block, fixed order; block sums land in out[b]. */
+__global__ void __launch_bounds__(256)
+k_kinetic(SpeciesDev sp, int nb, double *__restrict__ out)
+{
+	const int lane = threadIdx.x & 31;
+	const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	if(b >= nb) return;
+	const int cnt = sp.count[b];
+	const size_t base = (size_t) b * sp.cap;
+	double acc = 0.0;
+	for(int i = lane; i < cnt; i += 32)
+	{
+		double ux = sp.ux[base + i], uy = sp.uy[base + i];
+		acc += ux * ux + uy * uy;
+	}
+	for(int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(FULL, acc, o);
+	if(lane == 0) out[b] = acc;
+}
+
+/* Potential energy: per-row sum of rho*phi over the slab (reference src/sim.c:356-363) */
+__global__ void __launch_bounds__(256)
+k_potential(const double *__restrict__ rho, const double *__restrict__ phi, Geom g,
+		double *__restrict__ out)
+{
+	__shared__ double part[8];
+	const int y = blockIdx.x;
+	double acc = 0.0;
+	for(int x = threadIdx.x; x < g.nx; x += blockDim.x)
+		acc += rho[(size_t) y * g.S + x] * phi[(size_t) (y + 1) * g.S + x];
+	for(int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(FULL, acc, o);
+	if((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+	__syncthreads();
+	if(threadIdx.x == 0)
+	{
+		double s = 0.0;
+		for(int w = 0; w < (int) (blockDim.x >> 5); w++) s += part[w];
+		out[y] = s;
+	}
+}
+
+/* Fixed-order sum of n doubles by one CTA (n is a few thousand: block/row partials) */
+__global__ void __launch_bounds__(1024)
+k_sum(const double *__restrict__ in, int n, double *__restrict__ out)
+{
+	__shared__ double part[1024];
+	double acc = 0.0;
+	for(int i = threadIdx.x; i < n; i += blockDim.x) acc += in[i];
+	part[threadIdx.x] = acc;
+	__syncthreads();
+	for(int o = 512; o > 0; o >>= 1)
+	{
+		if((int) threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+		__syncthreads();
+	}
+	if(threadIdx.x == 0) *out = part[0];
+}
+
+/* Throughput-only initialiser: particle k of block b sits uniformly inside block b, so
+ * the plasma is uniform with equal block populations; u ~ U(-v, v) per axis as in the
+ * reference's "random position" (src/particle.c:72-73). Counter-based (splitmix64). */
+__device__ __forceinline__ double
+u01(uint64_t &s)
+{
+	s += 0x9e3779b97f4a7c15ULL;
+	uint64_t z = s;
+	z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+	z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+	z ^= z >> 31;
+	return (double) (z >> 11) * (1.0 / 9007199254740992.0);
+}
+
+__global__ void __launch_bounds__(256)
+k_init_uniform(SpeciesDev sp, Geom g, int nb, long long n, long long id0, double vx, double vy,
+		uint64_t seed)
+{
+	const int lane = threadIdx.x & 31;
+	const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	if(b >= nb) return;
+	const long long cnt = n / nb + (b < n % nb ? 1 : 0);
+	const size_t base = (size_t) b * sp.cap;
+	const int bx = b % g.nbx, by = b / g.nbx;
+	for(long long k = lane; k < cnt; k += 32)
+	{
+		long long gid = id0 + k * nb + b;
+		uint64_t s = seed ^ ((uint64_t) gid * 0xd1342543de82ef95ULL);
+		double fx = u01(s), fy = u01(s);
+		double x = ((double) (bx * g.BX) + fx * g.BX) * g.dx;
+		double y = g.y0 + ((double) (by * g.BY) + fy * g.BY) * g.dy;
+		/* keep the particle strictly inside its block whatever the rounding */
+		if(block_of(g, x, y) != b)
+		{
+			x = ((double) (bx * g.BX) + 0.5 * g.BX) * g.dx;
+			y = g.y0 + ((double) (by * g.BY) + 0.5 * g.BY) * g.dy;
+		}
+		sp.x[base + k] = x;
+		sp.y[base + k] = y;
+		sp.ux[base + k] = (2.0 * u01(s) - 1.0) * vx;
+		sp.uy[base + k] = (2.0 * u01(s) - 1.0) * vy;
+		sp.uz[base + k] = 0.0;
+		sp.id[base + k] = gid;
+	}
+	if(lane == 0) { sp.count[b] = (int) cnt; sp.ocount[b] = 0; }
+}
+
+#endif

@@ -1,0 +1,1040 @@
+/* cpic_b200: simulation context, stage orchestration and the C ABI (include/cpic_b200.h).
+ *
+ * Stage order and semantics follow the reference's sim_step (src/sim.c:481-581); every
+ * entry point names the reference function it replaces. Device work goes to one stream.
+ */
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cufft.h>
+
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "cpic_b200.h"
+#include "kernels.cuh"
+#include "comm.h"
+
+/* ------------------------------------------------------------------ errors */
+
+static thread_local char g_err[512] = "";
+
+static int
+fail(int code, const char *fmt, ...)
+{
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_err, sizeof(g_err), fmt, ap);
+	va_end(ap);
+	return code;
+}
+
+#define CK(call) do { cudaError_t e_ = (call); if(e_ != cudaSuccess) \
+	return fail(CPIC_B200_ECUDA, "%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); } while(0)
+#define CKFFT(call) do { cufftResult r_ = (call); if(r_ != CUFFT_SUCCESS) \
+	return fail(CPIC_B200_ECUDA, "%s:%d: %s: cufft error %d", __FILE__, __LINE__, #call, (int) r_); } while(0)
+
+extern "C" const char *cpic_b200_last_error(void) { return g_err; }
+extern "C" void cpic_b200_set_error_(const char *msg) { snprintf(g_err, sizeof(g_err), "%s", msg); }
+extern "C" const char *cpic_b200_version(void) { return "cpic_b200 0.1 (sm_100a)"; }
+
+/* ----------------------------------------------------------------- context */
+
+struct SpeciesHost {
+	SpeciesDev d;
+	void *block;             /* one allocation: x y ux uy uz id count (the "image") */
+	size_t block_bytes;
+	void *oblock;            /* outboxes */
+	double *pE;              /* optional per-particle E */
+	long long n;
+	double q, m;
+};
+
+enum { T_FIELD_E, T_PUSH, T_EXCHANGE, T_RHO, T_SOLVER, T_COUNT };
+
+struct cpic_b200_sim {
+	cpic_b200_params_t p;
+	Geom g;
+	int nb;                  /* particle blocks of the slab */
+	int nob;                 /* outbox blocks: nb (+ 2*nbx ghost rows with several ranks) */
+	long long iter;
+	double umax[3];
+	cudaStream_t stream;
+	int device;
+
+	double *rho, *phi, *phi_raw, *Ex, *Ey, *G;
+	cufftDoubleComplex *gk;
+	cufftHandle plan_fwd, plan_inv;
+	bool have_plans;
+	double *hb, *hr, *hc;    /* deposit halos */
+	double *red;             /* reduction scratch */
+	int *errflag;
+	int *h_err;              /* pinned */
+	CUtensorMap mapEx, mapEy;
+	size_t smem_push, smem_dep;
+
+	SpeciesHost sp[CPIC_B200_MAX_SPECIES];
+
+	Comm *comm;              /* NULL on one rank */
+
+	bool timing;
+	cudaEvent_t ev[2];
+	double ms[T_COUNT];
+	long long launches;
+};
+
+typedef cpic_b200_sim sim_t_;
+
+static int
+pick_div(long long n, int maxd)
+{
+	int d = maxd;
+	while(d > 1 && n % d) d >>= 1;
+	return d;
+}
+
+typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+		const cuuint64_t *, const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+		CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+		CUtensorMapFloatOOBfill);
+
+static int
+make_tensor_map(CUtensorMap *map, double *base, const Geom &g)
+{
+	static encode_fn encode = NULL;
+	if(!encode)
+	{
+		void *fn = NULL;
+		cudaDriverEntryPointQueryResult qres;
+		CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+		if(!fn || qres != cudaDriverEntryPointSuccess)
+			return fail(CPIC_B200_ECUDA, "cuTensorMapEncodeTiled is not available in this driver");
+		encode = (encode_fn) fn;
+	}
+	/* dim 0 = columns (contiguous), dim 1 = rows */
+	cuuint64_t dims[2] = { (cuuint64_t) g.SE, (cuuint64_t) (g.ny + 1) };
+	cuuint64_t strides[1] = { (cuuint64_t) g.SE * sizeof(double) };
+	cuuint32_t box[2] = { (cuuint32_t) g.TW, (cuuint32_t) g.TH };
+	cuuint32_t estr[2] = { 1, 1 };
+	CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, dims, strides, box, estr,
+			CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+			CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	if(r != CUDA_SUCCESS)
+		return fail(CPIC_B200_ECUDA, "cuTensorMapEncodeTiled failed (%d) for E tile %dx%d of %dx%d",
+				(int) r, g.TW, g.TH, g.SE, g.ny + 1);
+	return 0;
+}
+
+static size_t
+tile_bytes(const Geom &g)
+{
+	size_t b = (size_t) g.TH * g.TW * sizeof(double);
+	return (b + 127) & ~(size_t) 127;
+}
+
+extern "C" int
+cpic_b200_create(const cpic_b200_params_t *pp, cpic_b200_sim_t **out)
+{
+	if(!pp || !out) return fail(CPIC_B200_EINVAL, "null argument");
+	const cpic_b200_params_t &p = *pp;
+	if(p.nx < 1 || p.ny < 1 || p.nx > (1 << 30) || p.ny > (1 << 30))
+		return fail(CPIC_B200_EINVAL, "grid.points out of range");
+	if(p.nranks < 1 || p.rank < 0 || p.rank >= p.nranks)
+		return fail(CPIC_B200_EINVAL, "bad rank %d of %d", p.rank, p.nranks);
+	/* reference src/sim.c:116-130 */
+	if(p.ny % p.nranks)
+		return fail(CPIC_B200_EINVAL, "The number of grid points in Y %lld cannot be divided by the number of processes %d",
+				(long long) p.ny, p.nranks);
+	if(p.plasma_chunks < 1 || p.nx % p.plasma_chunks)
+		return fail(CPIC_B200_EINVAL, "The number of grid points in X %lld cannot be divided by the number of plasma chunks %lld",
+				(long long) p.nx, (long long) p.plasma_chunks);
+	if(p.nspecies < 1 || p.nspecies > CPIC_B200_MAX_SPECIES)
+		return fail(CPIC_B200_EINVAL, "between 1 and %d species are supported", CPIC_B200_MAX_SPECIES);
+	if(!(p.dt > 0) || !(p.Lx > 0) || !(p.Ly > 0) || !(p.e0 > 0))
+		return fail(CPIC_B200_EINVAL, "time_step, space_length and vacuum_permittivity must be positive");
+	if(p.nranks > 1 && (p.nx % 2))
+		return fail(CPIC_B200_EINVAL, "several ranks need an even number of grid points in X");
+
+	int ndev = 0;
+	if(cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+		return fail(CPIC_B200_ECUDA, "no CUDA device: cpic_b200 has no CPU path");
+	int dev = p.device;
+	if(dev < 0) CK(cudaGetDevice(&dev));
+	CK(cudaSetDevice(dev));
+
+	sim_t_ *s = new sim_t_();
+	memset(s, 0, sizeof(*s));
+	s->p = p;
+	s->device = dev;
+	if(s->p.capacity_factor <= 1.0) s->p.capacity_factor = 1.5;
+
+	Geom &g = s->g;
+	g.nx = (int) p.nx;
+	g.ny_glob = (int) p.ny;
+	g.ny = (int) (p.ny / p.nranks);
+	g.row0 = p.rank * g.ny;
+	g.S = 2 * (g.nx / 2 + 1);
+	g.BX = pick_div(g.nx, 8);
+	g.BY = pick_div(g.ny, 8);
+	g.nbx = g.nx / g.BX;
+	g.nby = g.ny / g.BY;
+	g.nby_glob = g.nby * p.nranks;
+	g.brow0 = p.rank * g.nby;
+	g.WPC = pick_div(g.nbx, MAX_WPC);
+	g.TW = g.WPC * g.BX + 2;
+	if(g.TW & 1) g.TW++;
+	g.TH = g.BY + 1;
+	g.tile_dbl = (int) ((((size_t) g.TH * g.TW * sizeof(double) + 127) & ~(size_t) 127) / sizeof(double));
+	g.SE = g.nx + 2;
+	if(g.SE & 1) g.SE++;
+	if(g.SE < g.TW) g.SE = g.TW;
+	g.Lx = p.Lx;
+	g.Ly = p.Ly;
+	g.dx = p.Lx / (double) p.nx;          /* reference src/sim.c:172-176 */
+	g.dy = p.Ly / (double) p.ny;
+	g.idx = 1.0 / g.dx;
+	g.idy = 1.0 / g.dy;
+	g.y0 = p.rank * (g.dy * g.ny);        /* reference src/field.c:37,149: rank * (dx[Y]*shape[Y]) */
+	s->nb = g.nbx * g.nby;
+	s->nob = s->nb + (p.nranks > 1 ? 2 * g.nbx : 0);
+	s->iter = -1;
+	/* reference src/sim.c:198-200 */
+	s->umax[0] = (double) (p.nx / p.plasma_chunks) * g.dx / p.dt;
+	s->umax[1] = (double) g.ny * g.dy / p.dt;
+	s->umax[2] = 1.0 * 0.0 / p.dt;
+
+#define CKD(call) do { cudaError_t e_ = (call); if(e_ != cudaSuccess) { \
+	int rc_ = fail(CPIC_B200_ECUDA, "%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+	cpic_b200_destroy(s); return rc_; } } while(0)
+
+	CKD(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+	CKD(cudaEventCreate(&s->ev[0]));
+	CKD(cudaEventCreate(&s->ev[1]));
+
+	const size_t nc = (size_t) g.nx / 2 + 1;
+	CKD(cudaMalloc(&s->rho, (size_t) (g.ny + 1) * g.S * sizeof(double)));
+	CKD(cudaMalloc(&s->phi, (size_t) (g.ny + 3) * g.S * sizeof(double)));
+	CKD(cudaMalloc(&s->phi_raw, (size_t) g.ny * g.S * sizeof(double)));
+	CKD(cudaMalloc(&s->Ex, (size_t) (g.ny + 1) * g.SE * sizeof(double)));
+	CKD(cudaMalloc(&s->Ey, (size_t) (g.ny + 1) * g.SE * sizeof(double)));
+	CKD(cudaMemset(s->rho, 0, (size_t) (g.ny + 1) * g.S * sizeof(double)));
+	CKD(cudaMemset(s->phi, 0, (size_t) (g.ny + 3) * g.S * sizeof(double)));
+	CKD(cudaMemset(s->Ex, 0, (size_t) (g.ny + 1) * g.SE * sizeof(double)));
+	CKD(cudaMemset(s->Ey, 0, (size_t) (g.ny + 1) * g.SE * sizeof(double)));
+	const int ncx = g.nbx / g.WPC;
+	CKD(cudaMalloc(&s->hb, (size_t) g.nby * g.nx * sizeof(double)));
+	CKD(cudaMalloc(&s->hr, (size_t) ncx * g.ny * sizeof(double)));
+	CKD(cudaMalloc(&s->hc, (size_t) g.nby * ncx * sizeof(double)));
+	CKD(cudaMalloc(&s->red, ((size_t) std::max(s->nb, g.ny) + 16) * sizeof(double)));
+	CKD(cudaMalloc(&s->errflag, sizeof(int)));
+	CKD(cudaMemset(s->errflag, 0, sizeof(int)));
+	CKD(cudaMallocHost(&s->h_err, sizeof(int)));
+
+	if(p.nranks == 1)
+	{
+		/* MFT_init, reference src/solver.c:207-335: the G table for all rows (one rank) */
+		std::vector<double> G((size_t) g.ny * nc);
+		const double cx = 2.0 * M_PI / (double) g.nx, cy = 2.0 * M_PI / (double) g.ny_glob;
+		for(int iy = 0; iy < g.ny; iy++)
+			for(size_t ix = 0; ix < nc; ix++)
+				G[(size_t) iy * nc + ix] = (ix == 0 && iy == 0) ? 0.0 :
+					1.0 / (2.0 * (cos(cx * (double) ix) + cos(cy * (double) iy)) - 4.0);
+		CKD(cudaMalloc(&s->G, G.size() * sizeof(double)));
+		CKD(cudaMemcpy(s->G, G.data(), G.size() * sizeof(double), cudaMemcpyHostToDevice));
+		CKD(cudaMalloc(&s->gk, (size_t) g.ny * nc * sizeof(cufftDoubleComplex)));
+
+		/* padded real rows of 2*(nx/2+1) doubles, as FFTW's r2c/c2r layout
+		 * (reference src/solver.c:314-330) */
+		int n[2] = { g.ny, g.nx };
+		int rembed[2] = { g.ny, g.S };
+		int cembed[2] = { g.ny, (int) nc };
+#define CKFD(call) do { cufftResult r_ = (call); if(r_ != CUFFT_SUCCESS) { \
+	int rc_ = fail(CPIC_B200_ECUDA, "%s:%d: %s: cufft error %d", __FILE__, __LINE__, #call, (int) r_); \
+	cpic_b200_destroy(s); return rc_; } } while(0)
+		CKFD(cufftPlanMany(&s->plan_fwd, 2, n, rembed, 1, g.ny * g.S, cembed, 1, g.ny * (int) nc, CUFFT_D2Z, 1));
+		CKFD(cufftPlanMany(&s->plan_inv, 2, n, cembed, 1, g.ny * (int) nc, rembed, 1, g.ny * g.S, CUFFT_Z2D, 1));
+		CKFD(cufftSetStream(s->plan_fwd, s->stream));
+		CKFD(cufftSetStream(s->plan_inv, s->stream));
+		s->have_plans = true;
+	}
+
+	int rc = make_tensor_map(&s->mapEx, s->Ex, g);
+	if(!rc) rc = make_tensor_map(&s->mapEy, s->Ey, g);
+	if(rc) { cpic_b200_destroy(s); return rc; }
+
+	s->smem_push = 128 + 2 * tile_bytes(g);
+	s->smem_dep = (size_t) g.WPC * (g.BX + 1) * (g.BY + 1) * sizeof(double);
+
+	for(int i = 0; i < p.nspecies; i++) { s->sp[i].q = p.q[i]; s->sp[i].m = p.m[i]; }
+
+	*out = s;
+	return 0;
+}
+
+static void
+free_species(SpeciesHost &h)
+{
+	cudaFree(h.block);
+	cudaFree(h.oblock);
+	cudaFree(h.pE);
+	double q = h.q, m = h.m;
+	memset(&h, 0, sizeof(h));
+	h.q = q; h.m = m;
+}
+
+extern "C" void
+cpic_b200_destroy(cpic_b200_sim_t *s)
+{
+	if(!s) return;
+	cudaSetDevice(s->device);
+	if(s->stream) cudaStreamSynchronize(s->stream);
+	for(int i = 0; i < CPIC_B200_MAX_SPECIES; i++) free_species(s->sp[i]);
+	if(s->comm) comm_destroy(s->comm);
+	if(s->have_plans) { cufftDestroy(s->plan_fwd); cufftDestroy(s->plan_inv); }
+	cudaFree(s->rho); cudaFree(s->phi); cudaFree(s->phi_raw); cudaFree(s->Ex); cudaFree(s->Ey);
+	cudaFree(s->G); cudaFree(s->gk); cudaFree(s->hb); cudaFree(s->hr); cudaFree(s->hc);
+	cudaFree(s->red); cudaFree(s->errflag);
+	if(s->h_err) cudaFreeHost(s->h_err);
+	if(s->ev[0]) cudaEventDestroy(s->ev[0]);
+	if(s->ev[1]) cudaEventDestroy(s->ev[1]);
+	if(s->stream) cudaStreamDestroy(s->stream);
+	delete s;
+}
+
+/* --------------------------------------------------------------- particles */
+
+static size_t
+align256(size_t v) { return (v + 255) & ~(size_t) 255; }
+
+static int ensure_particle_E(sim_t_ *s, int is);
+
+/* (Re)allocate one species with `cap` slots per block */
+static int
+alloc_species(sim_t_ *s, int is, int cap)
+{
+	SpeciesHost &h = s->sp[is];
+	free_species(h);
+	const size_t nslot = (size_t) s->nb * cap;
+	const size_t arr = align256(nslot * sizeof(double));
+	const size_t cnt = align256((size_t) s->nob * sizeof(int));
+	h.block_bytes = 6 * arr + cnt;
+	CK(cudaMalloc(&h.block, h.block_bytes));
+	CK(cudaMemsetAsync(h.block, 0, h.block_bytes, s->stream));
+	char *b = (char *) h.block;
+	h.d.x = (double *) (b + 0 * arr);
+	h.d.y = (double *) (b + 1 * arr);
+	h.d.ux = (double *) (b + 2 * arr);
+	h.d.uy = (double *) (b + 3 * arr);
+	h.d.uz = (double *) (b + 4 * arr);
+	h.d.id = (long long *) (b + 5 * arr);
+	h.d.count = (int *) (b + 6 * arr);
+	h.d.cap = cap;
+
+	int ocap = ((cap / 2 + 31) / 32) * 32;
+	if(ocap < 64) ocap = 64;
+	h.d.ocap = ocap;
+	const size_t oslot = (size_t) s->nob * ocap;
+	const size_t oarr = align256(oslot * sizeof(double));
+	const size_t oint = align256(oslot * sizeof(int));
+	const size_t ocnt = align256((size_t) s->nob * sizeof(int));
+	CK(cudaMalloc(&h.oblock, 6 * oarr + 2 * oint + ocnt));
+	CK(cudaMemsetAsync(h.oblock, 0, 6 * oarr + 2 * oint + ocnt, s->stream));
+	char *o = (char *) h.oblock;
+	h.d.ox = (double *) (o + 0 * oarr);
+	h.d.oy = (double *) (o + 1 * oarr);
+	h.d.oux = (double *) (o + 2 * oarr);
+	h.d.ouy = (double *) (o + 3 * oarr);
+	h.d.ouz = (double *) (o + 4 * oarr);
+	h.d.oid = (long long *) (o + 5 * oarr);
+	h.d.odest = (int *) (o + 6 * oarr);
+	h.d.ohole = (int *) (o + 6 * oarr + oint);
+	h.d.ocount = (int *) (o + 6 * oarr + 2 * oint);
+
+	if(s->p.keep_particle_E) return ensure_particle_E(s, is);
+	return 0;
+}
+
+static int
+ensure_particle_E(sim_t_ *s, int is)
+{
+	SpeciesHost &h = s->sp[is];
+	if(h.d.pEx || !h.block) return 0;
+	const size_t arr = align256((size_t) s->nb * h.d.cap * sizeof(double));
+	const size_t oarr = align256((size_t) s->nob * h.d.ocap * sizeof(double));
+	CK(cudaMalloc(&h.pE, 2 * arr + 2 * oarr));
+	CK(cudaMemsetAsync(h.pE, 0, 2 * arr + 2 * oarr, s->stream));
+	h.d.pEx = h.pE;
+	h.d.pEy = (double *) ((char *) h.pE + arr);
+	h.d.oEx = (double *) ((char *) h.pE + 2 * arr);
+	h.d.oEy = (double *) ((char *) h.pE + 2 * arr + oarr);
+	return 0;
+}
+
+static int
+cap_for(const sim_t_ *s, long long maxcount)
+{
+	long long c = (long long) ceil((double) maxcount * s->p.capacity_factor) + 64;
+	c = (c + 31) / 32 * 32;
+	if(c > (1LL << 30)) c = 1LL << 30;
+	return (int) c;
+}
+
+/* plasma_init + particle_comm_initial (reference src/plasma.c:292-316 and
+ * src/comm_plasma.c:1122-1142 in global mode): the host sorts the particles into their
+ * blocks with a stable counting sort (input order is kept inside a block) and uploads. */
+extern "C" int
+cpic_b200_set_particles(cpic_b200_sim_t *s, int is, int64_t n, const int64_t *id,
+		const double *x, const double *y, const double *ux, const double *uy, const double *uz)
+{
+	if(!s || is < 0 || is >= s->p.nspecies || n < 0) return fail(CPIC_B200_EINVAL, "bad species or count");
+	if(n > 0 && (!x || !y || !ux || !uy)) return fail(CPIC_B200_EINVAL, "null particle array");
+	CK(cudaSetDevice(s->device));
+	const Geom &g = s->g;
+	const double y1 = g.y0 + g.dy * g.ny;
+
+	std::vector<int> blk((size_t) n);
+	std::vector<int> cnt((size_t) s->nb, 0);
+	for(int64_t i = 0; i < n; i++)
+	{
+		if(!(x[i] >= 0.0 && x[i] <= g.Lx) || !(y[i] >= g.y0 && y[i] <= y1))
+			return fail(CPIC_B200_EINVAL, "particle %lld at (%g, %g) is outside this rank's slab [0,%g]x[%g,%g]",
+					(long long) i, x[i], y[i], g.Lx, g.y0, y1);
+		int b = block_of(g, x[i], y[i]);
+		blk[(size_t) i] = b;
+		cnt[(size_t) b]++;
+	}
+	int maxc = 0;
+	for(int b = 0; b < s->nb; b++) maxc = std::max(maxc, cnt[(size_t) b]);
+	/* leave room for the mean as well: a nearly empty start must not pin the capacity */
+	long long mean = s->nb ? (n + s->nb - 1) / s->nb : 0;
+	int cap = cap_for(s, std::max<long long>(maxc, mean));
+
+	SpeciesHost &h = s->sp[is];
+	if(!h.block || h.d.cap < cap)
+	{
+		int rc = alloc_species(s, is, cap);
+		if(rc) return rc;
+	}
+	cap = h.d.cap;
+
+	const size_t nslot = (size_t) s->nb * cap;
+	std::vector<double> hx(nslot, 0.0), hy(nslot, 0.0), hux(nslot, 0.0), huy(nslot, 0.0), huz(nslot, 0.0);
+	std::vector<long long> hid(nslot, 0);
+	std::vector<int> fill((size_t) s->nb, 0);
+	for(int64_t i = 0; i < n; i++)
+	{
+		int b = blk[(size_t) i];
+		size_t k = (size_t) b * cap + (size_t) fill[(size_t) b]++;
+		hx[k] = x[i]; hy[k] = y[i];
+		hux[k] = ux[i]; huy[k] = uy[i]; huz[k] = uz ? uz[i] : 0.0;
+		hid[k] = id ? id[i] : i;
+	}
+	CK(cudaMemcpyAsync(h.d.x, hx.data(), nslot * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+	CK(cudaMemcpyAsync(h.d.y, hy.data(), nslot * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+	CK(cudaMemcpyAsync(h.d.ux, hux.data(), nslot * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+	CK(cudaMemcpyAsync(h.d.uy, huy.data(), nslot * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+	CK(cudaMemcpyAsync(h.d.uz, huz.data(), nslot * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+	CK(cudaMemcpyAsync(h.d.id, hid.data(), nslot * sizeof(long long), cudaMemcpyHostToDevice, s->stream));
+	CK(cudaMemcpyAsync(h.d.count, cnt.data(), (size_t) s->nb * sizeof(int), cudaMemcpyHostToDevice, s->stream));
+	CK(cudaMemsetAsync(h.d.ocount, 0, (size_t) s->nob * sizeof(int), s->stream));
+	CK(cudaStreamSynchronize(s->stream));
+	h.n = n;
+	return 0;
+}
+
+extern "C" int
+cpic_b200_init_uniform(cpic_b200_sim_t *s, int is, int64_t n, int64_t id0, double vx, double vy, uint64_t seed)
+{
+	if(!s || is < 0 || is >= s->p.nspecies || n < 0) return fail(CPIC_B200_EINVAL, "bad species or count");
+	CK(cudaSetDevice(s->device));
+	long long per = (n + s->nb - 1) / s->nb;
+	int cap = cap_for(s, per);
+	SpeciesHost &h = s->sp[is];
+	if(!h.block || h.d.cap < cap)
+	{
+		int rc = alloc_species(s, is, cap);
+		if(rc) return rc;
+	}
+	k_init_uniform<<<(s->nb + 7) / 8, 256, 0, s->stream>>>(h.d, s->g, s->nb, n, id0, vx, vy, seed);
+	CK(cudaGetLastError());
+	CK(cudaMemsetAsync(h.d.ocount, 0, (size_t) s->nob * sizeof(int), s->stream));
+	h.n = n;
+	return 0;
+}
+
+extern "C" int64_t
+cpic_b200_num_particles(cpic_b200_sim_t *s, int is)
+{
+	if(!s || is < 0 || is >= s->p.nspecies) return -1;
+	SpeciesHost &h = s->sp[is];
+	if(!h.block) return 0;
+	cudaSetDevice(s->device);
+	std::vector<int> cnt((size_t) s->nb);
+	if(cudaMemcpyAsync(cnt.data(), h.d.count, cnt.size() * sizeof(int), cudaMemcpyDeviceToHost, s->stream) != cudaSuccess) return -1;
+	if(cudaStreamSynchronize(s->stream) != cudaSuccess) return -1;
+	long long n = 0;
+	for(int c : cnt) n += c;
+	return n;
+}
+
+extern "C" int64_t
+cpic_b200_get_particles(cpic_b200_sim_t *s, int is, int64_t capn, int64_t *id, double *x, double *y,
+		double *ux, double *uy, double *uz, double *Ex, double *Ey)
+{
+	if(!s || is < 0 || is >= s->p.nspecies) { fail(CPIC_B200_EINVAL, "bad species"); return -1; }
+	SpeciesHost &h = s->sp[is];
+	if(!h.block) return 0;
+	cudaSetDevice(s->device);
+	const int cap = h.d.cap;
+	std::vector<int> cnt((size_t) s->nb);
+	if(cudaMemcpyAsync(cnt.data(), h.d.count, cnt.size() * sizeof(int), cudaMemcpyDeviceToHost, s->stream) != cudaSuccess
+			|| cudaStreamSynchronize(s->stream) != cudaSuccess)
+	{ fail(CPIC_B200_ECUDA, "copy of block counts failed"); return -1; }
+	long long n = 0;
+	for(int c : cnt) n += c;
+	if(n > capn) return n;
+
+	const size_t nslot = (size_t) s->nb * cap;
+	std::vector<double> tmp(nslot);
+	struct { const void *src; double *dst; } arrs[] = {
+		{ h.d.x, x }, { h.d.y, y }, { h.d.ux, ux }, { h.d.uy, uy }, { h.d.uz, uz },
+		{ h.d.pEx, Ex }, { h.d.pEy, Ey }, { h.d.id, (double *) id } };
+	for(auto &a : arrs)
+	{
+		if(!a.dst) continue;
+		if(!a.src)
+		{
+			for(long long i = 0; i < n; i++) a.dst[i] = 0.0;
+			continue;
+		}
+		if(cudaMemcpy(tmp.data(), a.src, nslot * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess)
+		{ fail(CPIC_B200_ECUDA, "particle download failed"); return -1; }
+		size_t k = 0;
+		for(int b = 0; b < s->nb; b++)
+		{
+			memcpy(a.dst + k, tmp.data() + (size_t) b * cap, (size_t) cnt[(size_t) b] * sizeof(double));
+			k += (size_t) cnt[(size_t) b];
+		}
+	}
+	return n;
+}
+
+/* ------------------------------------------------------------------ timing */
+
+struct StageTimer {
+	sim_t_ *s; int which;
+	StageTimer(sim_t_ *s_, int w) : s(s_), which(w)
+	{
+		if(s->timing) cudaEventRecord(s->ev[0], s->stream);
+	}
+	~StageTimer()
+	{
+		if(!s->timing) return;
+		float ms = 0;
+		cudaEventRecord(s->ev[1], s->stream);
+		cudaEventSynchronize(s->ev[1]);
+		cudaEventElapsedTime(&ms, s->ev[0], s->ev[1]);
+		s->ms[which] += ms;
+	}
+};
+
+extern "C" int
+cpic_b200_timing(cpic_b200_sim_t *s, int enable)
+{
+	if(!s) return fail(CPIC_B200_EINVAL, "null sim");
+	s->timing = enable != 0;
+	memset(s->ms, 0, sizeof(s->ms));
+	s->launches = 0;
+	return 0;
+}
+
+extern "C" int
+cpic_b200_get_timing(cpic_b200_sim_t *s, double ms[5], int64_t launches[1])
+{
+	if(!s) return fail(CPIC_B200_EINVAL, "null sim");
+	if(ms) for(int i = 0; i < T_COUNT; i++) ms[i] = s->ms[i];
+	if(launches) launches[0] = s->launches;
+	return 0;
+}
+
+/* ------------------------------------------------------------------ stages */
+
+static int
+check_launch(sim_t_ *s, int n = 1)
+{
+	s->launches += n;
+	cudaError_t e = cudaGetLastError();
+	if(e != cudaSuccess) return fail(CPIC_B200_ECUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+	return 0;
+}
+
+/* MFT_solve, reference src/solver.c:465-509 (one rank: cuFFT D2Z, G multiply, Z2D;
+ * several ranks: comm.cu) */
+static int
+solve(sim_t_ *s)
+{
+	const Geom &g = s->g;
+	if(s->comm) return comm_solve(s->comm, s->rho, s->phi_raw, s->stream, &s->launches);
+	const size_t n = (size_t) g.ny * (g.nx / 2 + 1);
+	CKFFT(cufftExecD2Z(s->plan_fwd, s->rho, s->gk));
+	int blocks = (int) std::min<size_t>((n + 255) / 256, 148 * 16);
+	k_green<<<blocks, 256, 0, s->stream>>>(s->gk, s->G, n);
+	CKFFT(cufftExecZ2D(s->plan_inv, s->gk, s->phi_raw));
+	return check_launch(s, 1);      /* own kernels only; cuFFT's are not counted */
+}
+
+extern "C" int
+cpic_b200_solve(cpic_b200_sim_t *s)
+{
+	if(!s) return fail(CPIC_B200_EINVAL, "null sim");
+	CK(cudaSetDevice(s->device));
+	int rc = solve(s);
+	if(rc) return rc;
+	const Geom &g = s->g;
+	dim3 grid((g.S + 127) / 128, g.ny + 3);
+	k_phi_finish<<<grid, 128, 0, s->stream>>>(s->phi_raw, s->phi, g, (double) (int) ((long long) g.nx * g.ny_glob), 0);
+	return check_launch(s);
+}
+
+/* stage_field_E, reference src/field.c:450-501: solve, phi halo, E = -grad phi */
+extern "C" int
+cpic_b200_stage_field_E(cpic_b200_sim_t *s)
+{
+	if(!s) return fail(CPIC_B200_EINVAL, "null sim");
+	CK(cudaSetDevice(s->device));
+	const Geom &g = s->g;
+	int rc;
+	{
+		StageTimer ts(s, T_SOLVER);
+		rc = solve(s);
+		if(rc) return rc;
+	}
+	StageTimer t(s, T_FIELD_E);
+	dim3 grid((g.S + 127) / 128, g.ny + 3);
+	/* N is an int in the reference (src/solver.c:366, :494) */
+	const double N = (double) (int) ((long long) g.nx * g.ny_glob);
+	k_phi_finish<<<grid, 128, 0, s->stream>>>(s->phi_raw, s->phi, g, N, s->comm ? 0 : 1);
+	if((rc = check_launch(s))) return rc;
+	if(s->comm && (rc = comm_phi_halo(s->comm, s->phi, s->stream))) return rc;
+	dim3 gridE((g.SE + 127) / 128, g.ny + 1);
+	k_field_E<<<gridE, 128, 0, s->stream>>>(s->phi, s->Ex, s->Ey, g);
+	return check_launch(s);
+}
+
+static PushParams
+push_params(const sim_t_ *s, int is)
+{
+	PushParams pp;
+	const double q = s->sp[is].q, m = s->sp[is].m;
+	/* reference src/mover.c:204-225: iteration 0 rewinds the velocities half a step */
+	if(s->iter == 0) { pp.dt = -s->p.dt / 2; pp.set_r = 0; }
+	else { pp.dt = s->p.dt; pp.set_r = 1; }
+	pp.dtqm2 = 0.5 * pp.dt * q / m;
+	const double t[3] = { s->p.B[0] * pp.dtqm2, s->p.B[1] * pp.dtqm2, s->p.B[2] * pp.dtqm2 };
+	pp.tx = t[0]; pp.ty = t[1]; pp.tz = t[2];
+	pp.sx = 2.0 * t[0] / fma(t[0], t[0], 1.0);
+	pp.sy = 2.0 * t[1] / fma(t[1], t[1], 1.0);
+	pp.sz = 2.0 * t[2] / fma(t[2], t[2], 1.0);
+	pp.umax_x = s->umax[0]; pp.umax_y = s->umax[1]; pp.umax_z = s->umax[2];
+	return pp;
+}
+
+template <int MODE>
+static int
+launch_gather_push(sim_t_ *s, int is)
+{
+	SpeciesHost &h = s->sp[is];
+	if(!h.block) return 0;
+	const Geom &g = s->g;
+	static bool attr_set[3] = { false, false, false };
+	if(!attr_set[MODE] || s->smem_push > 48 * 1024)
+	{
+		CK(cudaFuncSetAttribute(k_gather_push<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) s->smem_push));
+		attr_set[MODE] = true;
+	}
+	const int ctas = s->nb / g.WPC;
+	k_gather_push<MODE><<<ctas, 32 * g.WPC, s->smem_push, s->stream>>>(h.d, g, push_params(s, is),
+			s->mapEx, s->mapEy, s->errflag);
+	return check_launch(s);
+}
+
+/* stage_plasma_E, reference src/particle.c:232-248 */
+extern "C" int
+cpic_b200_stage_plasma_E(cpic_b200_sim_t *s)
+{
+	if(!s) return fail(CPIC_B200_EINVAL, "null sim");
+	CK(cudaSetDevice(s->device));
+	StageTimer t(s, T_PUSH);
+	for(int is = 0; is < s->p.nspecies; is++)
+	{
+		int rc = ensure_particle_E(s, is);
+		if(!rc) rc = launch_gather_push<0>(s, is);
+		if(rc) return rc;
+	}
+	return 0;
+}
+
+/* comm_plasma, reference src/comm_plasma.c:1122-1142 */
+static int
+exchange(sim_t_ *s)
+{
+	StageTimer t(s, T_EXCHANGE);
+	for(int is = 0; is < s->p.nspecies; is++)
+	{
+		SpeciesHost &h = s->sp[is];
+		if(!h.block) continue;
+		if(s->comm)
+		{
+			int rc = comm_particles(s->comm, &h.d, s->g, s->nb, s->stream, s->errflag, &s->launches);
+			if(rc) return rc;
+		}
+		k_migrate<<<(s->nb + 7) / 8, 256, 0, s->stream>>>(h.d, s->g, s->nb, s->errflag);
+		int rc = check_launch(s);
+		if(rc) return rc;
+	}
+	return 0;
+}
+
+/* stage_plasma_r, reference src/mover.c:331-362: plasma_mover then comm_plasma */
+template <int MODE>
+static int
+stage_plasma_r(sim_t_ *s)
+{
+	{
+		StageTimer t(s, T_PUSH);
+		for(int is = 0; is < s->p.nspecies; is++)
+		{
+			int rc = 0;
+			if(MODE == 1) rc = ensure_particle_E(s, is);
+			if(!rc) rc = launch_gather_push<MODE>(s, is);
+			if(rc) return rc;
+		}
+	}
+	/* at iteration 0 nothing moves (src/mover.c:204-215), the exchange is a no-op */
+	if(s->iter == 0) return 0;
+	return exchange(s);
+}
+
+extern "C" int
+cpic_b200_stage_plasma_r(cpic_b200_sim_t *s)
+{
+	if(!s) return fail(CPIC_B200_EINVAL, "null sim");
+	CK(cudaSetDevice(s->device));
+	return stage_plasma_r<1>(s);
+}
+
+/* stage_field_rho, reference src/field.c:268-356 */
+extern "C" int
+cpic_b200_stage_field_rho(cpic_b200_sim_t *s)
+{
+	if(!s) return fail(CPIC_B200_EINVAL, "null sim");
+	CK(cudaSetDevice(s->device));
+	StageTimer t(s, T_RHO);
+	const Geom &g = s->g;
+	const int ctas = s->nb / g.WPC;
+	const int ncx = g.nbx / g.WPC;
+	bool first = true;
+	if(s->smem_dep > 48 * 1024)
+	{
+		CK(cudaFuncSetAttribute(k_deposit<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) s->smem_dep));
+		CK(cudaFuncSetAttribute(k_deposit<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) s->smem_dep));
+	}
+	for(int is = 0; is < s->p.nspecies; is++)
+	{
+		SpeciesHost &h = s->sp[is];
+		if(!h.block) continue;
+		const double vq = -h.q / s->p.e0;       /* reference src/interpolate.c:307 */
+		if(first) k_deposit<true><<<ctas, 32 * g.WPC, s->smem_dep, s->stream>>>(h.d, g, vq, s->rho, s->hb, s->hr, s->hc);
+		else k_deposit<false><<<ctas, 32 * g.WPC, s->smem_dep, s->stream>>>(h.d, g, vq, s->rho, s->hb, s->hr, s->hc);
+		first = false;
+		int rc = check_launch(s);
+		if(rc) return rc;
+	}
+	if(first)
+	{
+		/* no particles at all: rho_reset only */
+		CK(cudaMemsetAsync(s->rho, 0, (size_t) (g.ny + 1) * g.S * sizeof(double), s->stream));
+	}
+	else
+	{
+		k_stitch_rows<<<dim3((g.nx + 127) / 128, g.nby), 128, 0, s->stream>>>(s->rho, s->hb, s->hr, s->hc, g);
+		k_stitch_cols<<<dim3((g.ny + 127) / 128, ncx), 128, 0, s->stream>>>(s->rho, s->hr, g);
+		int rc = check_launch(s, 2);
+		if(rc) return rc;
+	}
+	/* comm_send_ghost_rho / comm_recv_ghost_rho, reference src/comm_field.c:51-136 */
+	if(s->comm)
+	{
+		int rc = comm_rho_halo(s->comm, s->rho, s->stream, &s->launches);
+		if(rc) return rc;
+	}
+	else
+	{
+		k_rho_fold<<<(g.nx + 127) / 128, 128, 0, s->stream>>>(s->rho, s->rho + (size_t) g.ny * g.S, g);
+		int rc = check_launch(s);
+		if(rc) return rc;
+	}
+	return 0;
+}
+
+/* sim_pre_step, reference src/sim.c:208-236 */
+extern "C" int
+cpic_b200_pre_step(cpic_b200_sim_t *s)
+{
+	if(!s) return fail(CPIC_B200_EINVAL, "null sim");
+	s->iter = -1;
+	int rc = cpic_b200_stage_field_rho(s);
+	if(!rc) rc = cpic_b200_stage_field_E(s);
+	s->iter = 0;
+	return rc;
+}
+
+/* sim_step, reference src/sim.c:481-581, gather and push fused */
+extern "C" int
+cpic_b200_step(cpic_b200_sim_t *s)
+{
+	if(!s) return fail(CPIC_B200_EINVAL, "null sim");
+	if(s->iter < 0) return fail(CPIC_B200_EINVAL, "call cpic_b200_pre_step first");
+	CK(cudaSetDevice(s->device));
+	int rc = cpic_b200_stage_field_E(s);
+	if(!rc) rc = stage_plasma_r<2>(s);
+	if(!rc) rc = cpic_b200_stage_field_rho(s);
+	if(rc) return rc;
+	s->iter++;
+	return 0;
+}
+
+extern "C" int
+cpic_b200_run(cpic_b200_sim_t *s, int64_t steps)
+{
+	for(int64_t i = 0; i < steps; i++)
+	{
+		int rc = cpic_b200_step(s);
+		if(rc) return rc;
+	}
+	return cpic_b200_sync(s);
+}
+
+/* `steps` sim_steps bracketed by CUDA events on the simulation's stream */
+extern "C" int
+cpic_b200_run_timed(cpic_b200_sim_t *s, int64_t steps, double *ms)
+{
+	if(!s || !ms) return fail(CPIC_B200_EINVAL, "null argument");
+	CK(cudaSetDevice(s->device));
+	cudaEvent_t a, b;
+	CK(cudaEventCreate(&a));
+	CK(cudaEventCreate(&b));
+	CK(cudaStreamSynchronize(s->stream));
+	CK(cudaEventRecord(a, s->stream));
+	int rc = 0;
+	for(int64_t i = 0; i < steps && !rc; i++) rc = cpic_b200_step(s);
+	CK(cudaEventRecord(b, s->stream));
+	CK(cudaEventSynchronize(b));
+	float t = 0;
+	CK(cudaEventElapsedTime(&t, a, b));
+	cudaEventDestroy(a);
+	cudaEventDestroy(b);
+	*ms = t;
+	if(rc) return rc;
+	return cpic_b200_sync(s);
+}
+
+extern "C" int64_t cpic_b200_iter(cpic_b200_sim_t *s) { return s ? s->iter : -1; }
+
+extern "C" int
+cpic_b200_set_iter(cpic_b200_sim_t *s, int64_t iter)
+{
+	if(!s) return fail(CPIC_B200_EINVAL, "null sim");
+	s->iter = iter;
+	return 0;
+}
+
+extern "C" int
+cpic_b200_sync(cpic_b200_sim_t *s)
+{
+	if(!s) return fail(CPIC_B200_EINVAL, "null sim");
+	CK(cudaSetDevice(s->device));
+	CK(cudaMemcpyAsync(s->h_err, s->errflag, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+	CK(cudaStreamSynchronize(s->stream));
+	const int e = *s->h_err;
+	if(!e) return 0;
+	CK(cudaMemsetAsync(s->errflag, 0, sizeof(int), s->stream));
+	if(e & ERRBIT_TMA) return fail(CPIC_B200_ECUDA, "a TMA tile load did not complete (tensor map rejected)");
+	if(e & ERRBIT_VELOCITY) return fail(CPIC_B200_EVELOCITY, "Max velocity exceeded (umax = %g %g %g)", s->umax[0], s->umax[1], s->umax[2]);
+	if(e & ERRBIT_FAR) return fail(CPIC_B200_EFAR, "a particle crossed more than one particle block (%dx%d cells) in one step", s->g.BX, s->g.BY);
+	return fail(CPIC_B200_ECAPACITY, "a particle block or outbox overflowed; raise capacity_factor (now %g)", s->p.capacity_factor);
+}
+
+/* ------------------------------------------------------------------ fields */
+
+static int
+field_geom(const sim_t_ *s, int f, double **base, int64_t *rows, int64_t *stride, int64_t *dstride)
+{
+	const Geom &g = s->g;
+	switch(f)
+	{
+		case CPIC_B200_RHO: *base = s->rho; *rows = g.ny + 1; *stride = g.S; *dstride = g.S; return 0;
+		case CPIC_B200_PHI: *base = s->phi; *rows = g.ny + 3; *stride = g.S; *dstride = g.S; return 0;
+		case CPIC_B200_EX: *base = s->Ex; *rows = g.ny + 1; *stride = g.nx; *dstride = g.SE; return 0;
+		case CPIC_B200_EY: *base = s->Ey; *rows = g.ny + 1; *stride = g.nx; *dstride = g.SE; return 0;
+	}
+	return fail(CPIC_B200_EINVAL, "unknown field %d", f);
+}
+
+extern "C" int
+cpic_b200_field_shape(cpic_b200_sim_t *s, int f, int64_t *rows, int64_t *stride)
+{
+	double *base = NULL; int64_t r = 0, st = 0, ds = 0;
+	if(!s) return fail(CPIC_B200_EINVAL, "null sim");
+	int rc = field_geom(s, f, &base, &r, &st, &ds);
+	if(rc) return rc;
+	if(rows) *rows = r;
+	if(stride) *stride = st;
+	return 0;
+}
+
+extern "C" int
+cpic_b200_get_field(cpic_b200_sim_t *s, int f, double *host)
+{
+	double *base = NULL; int64_t r = 0, st = 0, ds = 0;
+	if(!s || !host) return fail(CPIC_B200_EINVAL, "null argument");
+	CK(cudaSetDevice(s->device));
+	int rc = field_geom(s, f, &base, &r, &st, &ds);
+	if(rc) return rc;
+	CK(cudaMemcpy2DAsync(host, (size_t) st * sizeof(double), base, (size_t) ds * sizeof(double),
+				(size_t) st * sizeof(double), (size_t) r, cudaMemcpyDeviceToHost, s->stream));
+	CK(cudaStreamSynchronize(s->stream));
+	return 0;
+}
+
+extern "C" int
+cpic_b200_set_field(cpic_b200_sim_t *s, int f, const double *host)
+{
+	double *base = NULL; int64_t r = 0, st = 0, ds = 0;
+	if(!s || !host) return fail(CPIC_B200_EINVAL, "null argument");
+	CK(cudaSetDevice(s->device));
+	int rc = field_geom(s, f, &base, &r, &st, &ds);
+	if(rc) return rc;
+	CK(cudaMemcpy2DAsync(base, (size_t) ds * sizeof(double), host, (size_t) st * sizeof(double),
+				(size_t) st * sizeof(double), (size_t) r, cudaMemcpyHostToDevice, s->stream));
+	if(f == CPIC_B200_EX || f == CPIC_B200_EY)
+	{
+		/* wrap columns [nx, SE) repeat columns [0, SE-nx) */
+		const Geom &g = s->g;
+		for(int c = g.nx; c < g.SE; c++)
+			CK(cudaMemcpy2DAsync(base + c, (size_t) ds * sizeof(double), host + (c - g.nx) % g.nx,
+						(size_t) st * sizeof(double), sizeof(double), (size_t) r, cudaMemcpyHostToDevice, s->stream));
+	}
+	CK(cudaStreamSynchronize(s->stream));
+	return 0;
+}
+
+/* conservation_energy, reference src/sim.c:332-405 (compiled out there):
+ * KE = sum_s m_s/2 sum(ux^2+uy^2), PE = sum rho*phi over the slab */
+extern "C" int
+cpic_b200_energy(cpic_b200_sim_t *s, double *kinetic, double *potential)
+{
+	if(!s) return fail(CPIC_B200_EINVAL, "null sim");
+	CK(cudaSetDevice(s->device));
+	const Geom &g = s->g;
+	double ke = 0.0, pe = 0.0, v;
+	double *res = s->red + std::max(s->nb, g.ny);
+	for(int is = 0; is < s->p.nspecies; is++)
+	{
+		SpeciesHost &h = s->sp[is];
+		if(!h.block) continue;
+		k_kinetic<<<(s->nb + 7) / 8, 256, 0, s->stream>>>(h.d, s->nb, s->red);
+		k_sum<<<1, 1024, 0, s->stream>>>(s->red, s->nb, res);
+		CK(cudaMemcpyAsync(&v, res, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+		CK(cudaStreamSynchronize(s->stream));
+		ke += v * h.m / 2.0;
+	}
+	k_potential<<<g.ny, 256, 0, s->stream>>>(s->rho, s->phi, g, s->red);
+	k_sum<<<1, 1024, 0, s->stream>>>(s->red, g.ny, res);
+	CK(cudaMemcpyAsync(&v, res, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+	CK(cudaStreamSynchronize(s->stream));
+	pe = v;
+	if(kinetic) *kinetic = ke;
+	if(potential) *potential = pe;
+	return 0;
+}
+
+/* -------------------------------------------------- raw images (bench e2e) */
+
+extern "C" int64_t
+cpic_b200_image_bytes(cpic_b200_sim_t *s)
+{
+	if(!s) return -1;
+	int64_t n = 0;
+	for(int is = 0; is < s->p.nspecies; is++) n += (int64_t) s->sp[is].block_bytes;
+	return n;
+}
+
+extern "C" int
+cpic_b200_image_download(cpic_b200_sim_t *s, void *host, int64_t bytes)
+{
+	if(!s || !host || bytes < cpic_b200_image_bytes(s)) return fail(CPIC_B200_EINVAL, "image buffer too small");
+	CK(cudaSetDevice(s->device));
+	char *p = (char *) host;
+	for(int is = 0; is < s->p.nspecies; is++)
+	{
+		SpeciesHost &h = s->sp[is];
+		if(!h.block) continue;
+		CK(cudaMemcpyAsync(p, h.block, h.block_bytes, cudaMemcpyDeviceToHost, s->stream));
+		p += h.block_bytes;
+	}
+	CK(cudaStreamSynchronize(s->stream));
+	return 0;
+}
+
+extern "C" int
+cpic_b200_image_upload(cpic_b200_sim_t *s, const void *host, int64_t bytes)
+{
+	if(!s || !host || bytes < cpic_b200_image_bytes(s)) return fail(CPIC_B200_EINVAL, "image buffer too small");
+	CK(cudaSetDevice(s->device));
+	const char *p = (const char *) host;
+	for(int is = 0; is < s->p.nspecies; is++)
+	{
+		SpeciesHost &h = s->sp[is];
+		if(!h.block) continue;
+		CK(cudaMemcpyAsync(h.block, p, h.block_bytes, cudaMemcpyHostToDevice, s->stream));
+		p += h.block_bytes;
+	}
+	return 0;
+}
+
+extern "C" void *
+cpic_b200_host_alloc(size_t bytes)
+{
+	void *p = NULL;
+	if(cudaMallocHost(&p, bytes) != cudaSuccess) return NULL;
+	return p;
+}
+
+extern "C" void cpic_b200_host_free(void *p) { if(p) cudaFreeHost(p); }
+
+/* ---------------------------------------------------------------- multi-GPU */
+
+extern "C" int
+cpic_b200_comm_id(void *id128)
+{
+	if(!id128) return fail(CPIC_B200_EINVAL, "null id");
+	return comm_unique_id(id128, g_err, sizeof(g_err));
+}
+
+extern "C" int
+cpic_b200_comm_init(cpic_b200_sim_t *s, const void *id128)
+{
+	if(!s || !id128) return fail(CPIC_B200_EINVAL, "null argument");
+	if(s->p.nranks == 1) return 0;
+	CK(cudaSetDevice(s->device));
+	if(s->comm) return fail(CPIC_B200_EINVAL, "communicator already initialised");
+	s->comm = comm_create(id128, s->p.rank, s->p.nranks, s->g, s->stream, g_err, sizeof(g_err));
+	if(!s->comm) return CPIC_B200_ECUDA;
+	return 0;
+}

@@ -1,0 +1,181 @@
+"""GPU parity tests: the CUDA path through the C ABI against the oracle on identical
+initial conditions. Tolerance: 1e-12 relative (BASELINE.json north_star) in the norms of
+SURVEY 8c: max|a-b|/max|b| per field, |dx|/L and |du|/max|u| per particle."""
+import numpy as np
+import pytest
+
+from conftest import conf_path
+from _parity import (TOL, relerr, pair_from_conf, oracle_from, gpu_from, field_errors, particle_errors,
+                     assert_close)
+from cpic_b200 import Sim, Params, load_conf, init_particles
+
+pytestmark = pytest.mark.gpu
+
+CONFS = ["uniform-small.conf", "2d-2species-small.conf", "2d-2species-delta.conf", "two-streams.conf",
+         "harmonic-64.conf", "cyclotron.conf"]
+
+
+@pytest.mark.parametrize("shape", [(64, 64), (128, 32), (4, 4), (8, 16), (256, 128)])
+def test_solver_parity(shape):
+    """MFT_solve (src/solver.c:465-509): cuFFT + k_green against the oracle's FFT."""
+    nx, ny = shape
+    p = Params(nx, ny, 4.0, 4.0 * ny / nx, 0.01, 1.0)
+    g = Sim(p)
+    o = oracle_from(p, [])
+    rho = np.random.default_rng(nx * 1000 + ny).standard_normal((ny + 1, nx))
+    raw = np.zeros(g.field_shape("rho"))
+    raw[:, :nx] = rho
+    g.set_raw_field("rho", raw)
+    o.set_rho(rho)
+    g.solve()
+    g.sync()
+    o.solve()
+    assert relerr(g.field("phi"), o.field("phi")) <= TOL
+
+
+@pytest.mark.parametrize("shape", [(64, 64), (4, 4), (16, 8)])
+def test_stage_field_E_parity(shape):
+    """stage_field_E (src/field.c:450-501): solve + phi ghosts + centred difference."""
+    nx, ny = shape
+    p = Params(nx, ny, 2.0, 2.0 * ny / nx, 0.01, 1.0)
+    g = Sim(p)
+    o = oracle_from(p, [])
+    rho = np.random.default_rng(7).standard_normal((ny + 1, nx))
+    raw = np.zeros(g.field_shape("rho"))
+    raw[:, :nx] = rho
+    g.set_raw_field("rho", raw)
+    o.set_rho(rho)
+    g.stage_field_E()
+    g.sync()
+    o.stage_field_E()
+    assert_close(field_errors(g, o, ("phi_ghost", "Ex", "Ey")), what=f"stage_field_E {shape}")
+
+
+@pytest.mark.parametrize("conf", CONFS)
+def test_deposit_parity(conf):
+    """stage_field_rho (src/field.c:268-356) right after the upload."""
+    g, o, params, _ = pair_from_conf(conf_path(conf))
+    g.sync()
+    assert_close(field_errors(g, o, ("rho_ghost",)), what=conf)
+    # total deposited charge: every particle contributes exactly -q/e0
+    tot = sum(-q / params.e0 * len(o.particles(i)["id"]) for i, q in enumerate(params.q))
+    got = g.field("rho").sum()
+    assert abs(got - tot) <= 1e-9 * max(1.0, abs(tot))
+
+
+@pytest.mark.parametrize("conf", CONFS)
+def test_first_10_steps_staged(conf):
+    """The four stage calls, separately, for iterations 0..9 (0 is the rewind
+    step), compared after every stage-complete step. Includes the per-particle E."""
+    g, o, params, _ = pair_from_conf(conf_path(conf))
+    assert_close(field_errors(g, o), what=f"{conf} after sim_init")
+    for it in range(10):
+        g.step_staged()
+        o.step()
+        g.sync()
+        assert_close(field_errors(g, o), what=f"{conf} fields, iteration {it}")
+        assert_close(particle_errors(g, o, params, with_E=True), what=f"{conf} particles, iteration {it}")
+
+
+@pytest.mark.parametrize("conf", CONFS)
+def test_first_10_steps_fused(conf):
+    """cpic_b200_step (gather+push fused, E never stored) for iterations 0..9."""
+    g, o, params, _ = pair_from_conf(conf_path(conf))
+    for it in range(10):
+        g.step()
+        o.step()
+        g.sync()
+        assert_close(field_errors(g, o), what=f"{conf} fields, iteration {it}")
+        assert_close(particle_errors(g, o, params), what=f"{conf} particles, iteration {it}")
+    assert g.iter == 10
+
+
+def test_fused_equals_staged_bitwise():
+    """Fusing gather into the push must not change a single bit."""
+    a, _, params, _ = pair_from_conf(conf_path("2d-2species-small.conf"))
+    b, _, _, _ = pair_from_conf(conf_path("2d-2species-small.conf"))
+    for _ in range(6):
+        a.step()
+        b.step_staged()
+    for i in range(len(params.q)):
+        pa, pb = a.particles(i, sort=False), b.particles(i, sort=False)
+        for k in ("id", "x", "y", "ux", "uy", "uz"):
+            assert np.array_equal(pa[k], pb[k]), (i, k, np.abs(pa[k] - pb[k]).max())
+    for name in ("rho", "phi", "Ex", "Ey"):
+        assert np.array_equal(a.raw_field(name), b.raw_field(name)), name
+
+
+def test_run_to_run_determinism():
+    """Sums are ordered: two runs give identical bits, particle order included."""
+    runs = []
+    for _ in range(2):
+        g, _, params, _ = pair_from_conf(conf_path("uniform-small.conf"))
+        for _ in range(12):
+            g.step()
+        g.sync()
+        runs.append(([g.raw_field(n) for n in ("rho", "phi", "Ex", "Ey")],
+                     [g.particles(i, sort=False) for i in range(len(params.q))]))
+        g.close()
+    for fa, fb in zip(runs[0][0], runs[1][0]):
+        assert np.array_equal(fa, fb)
+    for pa, pb in zip(runs[0][1], runs[1][1]):
+        for k in pa:
+            assert np.array_equal(pa[k], pb[k]), k
+
+
+def test_hot_beam_migration():
+    """comm_plasma (src/comm_plasma.c:1122-1142): a beam that crosses about one cell per step
+    in both directions, so that a large share of every particle block migrates each step."""
+    nx = ny = 64
+    n = 30000
+    rng = np.random.default_rng(5)
+    L = 8.0
+    dx = L / nx
+    dt = 0.05
+    p = Params(nx, ny, L, L, dt, 1.0e6, (0.0, 0.0, 0.2), (-1.0,), (1.0,), plasma_chunks=1)
+    v = 0.9 * dx / dt
+    parts = [{"id": np.arange(n), "x": rng.uniform(0, L, n), "y": rng.uniform(0, L, n),
+              "ux": rng.choice([-v, v], n), "uy": rng.choice([-v, v], n)}]
+    o = oracle_from(p, parts)
+    g = gpu_from(p, parts)
+    o.pre_step()
+    g.pre_step()
+    for it in range(20):
+        g.step()
+        o.step()
+        g.sync()
+        assert g.num_particles(0) == n
+        assert_close(field_errors(g, o), what=f"hot beam fields, iteration {it}")
+        assert_close(particle_errors(g, o, p), what=f"hot beam particles, iteration {it}")
+
+
+def test_velocity_limit_is_reported():
+    """check_velocity (src/mover.c:97-137) aborts in the reference; here it is an error code."""
+    from cpic_b200 import Cpic_b200Error
+    p = Params(16, 16, 1.0, 1.0, 1.0, 1.0, (0, 0, 0), (-1.0,), (1.0,), plasma_chunks=16)
+    parts = [{"id": np.arange(4), "x": np.full(4, 0.5), "y": np.full(4, 0.5),
+              "ux": np.full(4, 100.0), "uy": np.zeros(4)}]
+    g = gpu_from(p, parts)
+    g.pre_step()
+    g.step()
+    with pytest.raises(Cpic_b200Error) as e:
+        g.sync()
+    assert e.value.code == 3
+
+
+def test_empty_and_ragged_species():
+    """A species with zero particles and one with a single particle (tail-pack cases of
+    src/interpolate.c:329-344 have no analogue here, but empty blocks must work)."""
+    p = Params(32, 16, 2.0, 1.0, 0.01, 1.0, (0, 0, 0.1), (-1.0, 1.0), (1.0, 4.0))
+    parts = [{"id": np.zeros(0, np.int64), "x": np.zeros(0), "y": np.zeros(0), "ux": np.zeros(0), "uy": np.zeros(0)},
+             {"id": np.array([7]), "x": np.array([1.99]), "y": np.array([0.999]), "ux": np.array([0.5]), "uy": np.array([0.7])}]
+    o = oracle_from(p, parts)
+    g = gpu_from(p, parts)
+    o.pre_step()
+    g.pre_step()
+    for it in range(8):
+        g.step_staged()
+        o.step()
+        g.sync()
+        assert_close(field_errors(g, o), what=f"ragged, iteration {it}")
+        assert_close(particle_errors(g, o, p, with_E=True), what=f"ragged particles, iteration {it}")

@@ -1,0 +1,68 @@
+"""The reference's own physics tests (test/cyclotron.c, test/constant-speed.c,
+test/harmonic.c + test/harmonic/harm.*) driven through the CUDA path."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import conf_path, ROOT
+from cpic_b200 import Sim
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def test_cyclotron():
+    """test/cyclotron.c:199-215, :317-322: position error against R(cos wt, sin wt) must stay
+    below v*dt^2 (the reference's limit) over the first 2000 of the 5000 cycles."""
+    g = Sim.from_conf(conf_path("cyclotron.conf"))
+    p = g.particles(0)
+    q, m, Bz = g.params.q[0], g.params.m[0], g.params.B[2]
+    dt = g.params.dt
+    # cyclotron_postinit, test/cyclotron.c:80-134
+    u = np.array([p["ux"][0], p["uy"][0], 0.0])
+    v = np.linalg.norm(u)
+    freq = abs(q) * Bz / m
+    radius = v / freq
+    tmp = np.cross(u, np.array(g.params.B))
+    tmp *= radius / np.linalg.norm(tmp)
+    center = np.array([p["x"][0], p["y"][0], 0.0]) + tmp
+    limit = v * dt * dt
+    worst = 0.0
+    for _ in range(2000):
+        g.step()
+        pp = g.particles(0)
+        r = np.hypot(pp["x"][0] - center[0], pp["y"][0] - center[1])
+        worst = max(worst, abs(r - abs(radius)))
+    assert worst < limit, (worst, limit)
+
+
+def test_constant_speed():
+    """test/constant-speed.c:13,:78-91: a lone charge feels no self force; its velocity must
+    not change by more than 1e-10."""
+    g = Sim.from_conf(conf_path("constant-speed.conf"))
+    u0 = g.particles(0)
+    for _ in range(300):
+        g.step()
+    g.sync()
+    u1 = g.particles(0)
+    # iteration 0 rewinds half a step with E = 0 on a lone particle: u is unchanged
+    assert abs(u1["ux"][0] - u0["ux"][0]) < 1e-10
+    assert abs(u1["uy"][0] - u0["uy"][0]) < 1e-10
+
+
+def test_harmonic_golden():
+    """test/harmonic.c prints r and E of particle 0 every step; the reference keeps 1200 of them
+    in test/harmonic/harm.r0x and harm.E0x (7 significant digits, 1024^2 grid)."""
+    r0 = np.loadtxt(os.path.join(GOLDEN, "harm.r0x"))
+    E0 = np.loadtxt(os.path.join(GOLDEN, "harm.E0x"))
+    g = Sim.from_conf(conf_path("harmonic.conf"))
+    xs, Es = [], []
+    nsteps = 300
+    for _ in range(nsteps):
+        g.step_staged()
+        p = g.particles(0)
+        xs.append(p["x"][0])
+        Es.append(p["Ex"][0])
+    assert np.abs(np.array(xs) - r0[:nsteps]).max() < 1e-6
+    assert np.abs(np.array(Es) - E0[:nsteps]).max() < 1e-8
