@@ -32,7 +32,8 @@ class ParamsC(C.Structure):
                 ("plasma_chunks", C.c_int64), ("nspecies", C.c_int32),
                 ("q", C.c_double * MAX_SPECIES), ("m", C.c_double * MAX_SPECIES),
                 ("rank", C.c_int32), ("nranks", C.c_int32), ("device", C.c_int32),
-                ("capacity_factor", C.c_double), ("keep_particle_E", C.c_int32)]
+                ("capacity_factor", C.c_double), ("keep_particle_E", C.c_int32),
+                ("outbox_fraction", C.c_double)]
 
 
 class RunC(C.Structure):

@@ -7,5 +7,5 @@ Comm *comm_create(const void *, int, int, const Geom &, cudaStream_t, char *err,
 void comm_destroy(Comm *) {}
 int comm_rho_halo(Comm *, double *, cudaStream_t, long long *) { return 2; }
 int comm_phi_halo(Comm *, double *, cudaStream_t) { return 2; }
-int comm_particles(Comm *, SpeciesDev *, const Geom &, int, cudaStream_t, int *, long long *) { return 2; }
+int comm_particles(Comm *, SpeciesDev *, int, const Geom &, int, cudaStream_t, int *, long long *) { return 2; }
 int comm_solve(Comm *, const double *, double *, cudaStream_t, long long *) { return 2; }

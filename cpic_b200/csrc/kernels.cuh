@@ -1,12 +1,15 @@
 /* Device kernels of the cpic_b200 hot path (sm_100a).
  *
  * Particle storage ("particle blocks"): every species is a set of fixed-capacity SoA
- * segments, one per block of BX x BY grid cells; segment b holds exactly the particles
- * whose cell lies in block b, in a deterministic order. One warp owns one particle
- * block for the duration of a kernel and walks it sequentially in batches of 32, so
- * every running count, compaction and floating point sum inside a block has a fixed
- * order; blocks only meet through fixed-order reads of neighbour outboxes / halo
- * arrays. No floating point atomics are used anywhere.
+ * segments, one per block of BX x BY grid cells. The particles whose cell lies in block
+ * b are its own segment plus the runs that its eight neighbours left for it in their
+ * outboxes during the last push ("arrivals"); they are never copied just to be moved:
+ * the next push streams over segment and arrivals alike, writes the particles that stay
+ * back into the segment (compacted, in place) and the ones that leave into its own
+ * outbox. One warp owns one particle block for the duration of a kernel and walks it
+ * sequentially in batches of 32, so every running count, compaction and floating point
+ * sum has a fixed order; blocks only meet through fixed-order reads of neighbour
+ * outboxes / halo arrays. No floating point atomics are used anywhere.
  */
 #ifndef CPIC_B200_KERNELS_CUH
 #define CPIC_B200_KERNELS_CUH
@@ -21,21 +24,42 @@
 #define FULL 0xffffffffu
 #define MAX_WPC 8
 
+/* Outbox of every block: the particles that left it in one push, one region per
+ * destination code (geom.h) so that the receiving block finds its arrivals as contiguous
+ * runs: four side regions of `ocs` slots (codes 1,3,5,7) and four corner regions of
+ * `occ` slots (codes 0,2,6,8), `obox` slots per block. Two of them alternate: a push
+ * reads the arrivals of the previous push from one and fills the other. */
+struct Outbox {
+	double *x, *y, *ux, *uy, *uz;
+	double *Ex, *Ey;         /* travel with the particle when the per-particle E is kept */
+	long long *id;
+	int *count;              /* 9 per block: leavers per destination code ([4] unused) */
+};
+
 /* Device view of one species */
 struct SpeciesDev {
 	double *x, *y, *ux, *uy, *uz;
-	double *pEx, *pEy;       /* gathered field per particle, optional (may be NULL) */
+	double *pEx, *pEy;       /* gathered field per particle, optional (ppack.E, reference src/def.h:96) */
 	long long *id;
-	int *count;              /* particles per block */
-	/* outbox: particles that left the block in the last push, in block order */
-	double *ox, *oy, *oux, *ouy, *ouz;
-	double *oEx, *oEy;       /* travel with the particle when pEx is kept (ppack.E, reference src/def.h:96) */
-	long long *oid;
-	int *odest;              /* destination code (geom.h) */
-	int *ohole;              /* slot the particle vacated */
-	int *ocount;
-	int cap, ocap;
+	int *count;              /* particles in the block's own segment */
+	Outbox ob[2];
+	int cap, ocs, occ, obox;
 };
+
+/* First slot of the region of destination code c inside a block's outbox */
+__host__ __device__ __forceinline__ int
+region_base(const SpeciesDev &sp, int c)
+{
+	const int sides = (c > 1) + (c > 3) + (c > 5) + (c > 7);
+	const int corners = (c > 0) + (c > 2) + (c > 6);
+	return sides * sp.ocs + corners * sp.occ;
+}
+
+__host__ __device__ __forceinline__ int
+region_cap(const SpeciesDev &sp, int c)
+{
+	return (c & 1) ? sp.ocs : sp.occ;
+}
 
 /* Everything the mover needs besides the particle (reference src/mover.c:191-226) */
 struct PushParams {
@@ -245,19 +269,85 @@ tile_gather(const double *t, int TW, int lx, int ly, double w00, double w01, dou
 	return v;
 }
 
+/* The arrivals of block b: lane k < 9 (k != 4) looks at neighbour k, which sits at
+ * (k%3-1, k/3-1) and addressed b with code 8-k. With several ranks the block rows -1 and
+ * nby are ghost outboxes filled from the neighbour ranks. Returns the total; every lane
+ * gets the nine run starts (exclusive prefix) and source blocks in registers. */
+struct Arrivals {
+	int start[9];
+	int src[9];
+	int total;
+};
+
+__device__ __forceinline__ Arrivals
+find_arrivals(const Outbox &in, const Geom &g, int nb, int b, int lane)
+{
+	const int bx = b % g.nbx, by = b / g.nbx;
+	int src = 0, a_k = 0;
+	if(lane < 9 && lane != DEST_STAY)
+	{
+		const int ndx = lane % 3 - 1, ndy = lane / 3 - 1;
+		int nbx_ = bx + ndx, nby_ = by + ndy;
+		if(nbx_ < 0) nbx_ += g.nbx; else if(nbx_ >= g.nbx) nbx_ -= g.nbx;
+		if(g.nby_glob == g.nby)
+		{
+			if(nby_ < 0) nby_ += g.nby; else if(nby_ >= g.nby) nby_ -= g.nby;
+			src = nby_ * g.nbx + nbx_;
+		}
+		else if(nby_ < 0) src = nb + nbx_;                 /* north ghost row */
+		else if(nby_ >= g.nby) src = nb + g.nbx + nbx_;    /* south ghost row */
+		else src = nby_ * g.nbx + nbx_;
+		a_k = in.count[(size_t) src * 9 + (8 - lane)];
+	}
+	int apre = a_k;
+	for(int o = 1; o < 16; o <<= 1)
+	{
+		const int ta = __shfl_up_sync(FULL, apre, o);
+		if(lane >= o) apre += ta;
+	}
+	Arrivals A;
+	A.total = __shfl_sync(FULL, apre, 8);
+	apre -= a_k;
+#pragma unroll
+	for(int k = 0; k < 9; k++)
+	{
+		A.start[k] = __shfl_sync(FULL, apre, k);
+		A.src[k] = __shfl_sync(FULL, src, k);
+	}
+	return A;
+}
+
+/* Outbox slot of arrival f (0 <= f < A.total) */
+__device__ __forceinline__ size_t
+arrival_slot(const Arrivals &A, const SpeciesDev &sp, int f)
+{
+	int k = 0;
+#pragma unroll
+	for(int q = 1; q < 9; q++) if(f >= A.start[q]) k = q;
+	int sb = 0, st = 0;
+#pragma unroll
+	for(int q = 0; q < 9; q++) if(q == k) { sb = A.src[q]; st = A.start[q]; }
+	return (size_t) sb * sp.obox + region_base(sp, 8 - k) + (f - st);
+}
+
 /* MODE 0: stage_plasma_E alone   (gather, store E per particle)
- * MODE 1: stage_plasma_r alone   (push from the stored per-particle E)
- * MODE 2: both fused             (gather + push; E kept per particle when pEx != NULL)
+ * MODE 1: stage_plasma_r alone   (push from the stored per-particle E, then exchange)
+ * MODE 2: both fused             (gather + push + exchange; E kept when pEx != NULL)
  *
- * One warp per particle block, WPC blocks of one block row per CTA sharing one E tile
- * fetched by TMA. After the push a particle whose cell left the block is appended to
- * the block's outbox (with the slot it vacated) and its slot is poisoned with NaN; the
- * others are written back in place. */
+ * plasma_mover and comm_plasma (reference src/mover.c:229-246, src/comm_plasma.c:1122-1142)
+ * in one pass. One warp per particle block, WPC blocks of one block row per CTA sharing
+ * one E tile fetched by TMA. The warp streams over the block's own segment and then
+ * over its arrivals (outbox `cur^1`), in batches of 32 with the next batch's loads
+ * already in flight. A particle that stays in the block is written back to the
+ * segment at the running write cursor (in place: the cursor never passes the read
+ * position); one that leaves goes to the region of its destination in outbox `cur`.
+ * Ranks inside a batch come from ballots, so the order is: batches in order, lanes in
+ * order. MODE 0 moves nothing. */
 template <int MODE>
-__global__ void __launch_bounds__(32 * MAX_WPC)
+__global__ void __launch_bounds__(32 * MAX_WPC, 3)
 k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 		const __grid_constant__ CUtensorMap mapEx, const __grid_constant__ CUtensorMap mapEy,
-		int *__restrict__ errflag)
+		int nb, int cur, int *__restrict__ errflag)
 {
 	extern __shared__ __align__(128) unsigned char smem[];
 	uint64_t *bar = (uint64_t *) smem;
@@ -265,21 +355,56 @@ k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 	double *tEy = tEx + g.tile_dbl;
 
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const unsigned lt = (1u << lane) - 1;
 	const int ncx = g.nbx / g.WPC;
 	const int by = blockIdx.x / ncx, cx = blockIdx.x % ncx;
 	const int bx = cx * g.WPC + warp;
 	const int b = by * g.nbx + bx;
 
+	if(MODE != 1 && threadIdx.x == 0)
+	{
+		mbar_init(bar, 1);
+		uint32_t bytes = 2u * (uint32_t) (g.TH * g.TW) * 8u;
+		mbar_expect_tx(bar, bytes);
+		tma_load_2d(tEx, &mapEx, cx * g.WPC * g.BX, by * g.BY, bar);
+		tma_load_2d(tEy, &mapEy, cx * g.WPC * g.BX, by * g.BY, bar);
+	}
+
+	/* MODE 0 leaves the arrivals where they are (outbox `cur`); a push consumes the
+	 * previous push's outbox and fills `cur` */
+	const Outbox &in = sp.ob[MODE == 0 ? cur : cur ^ 1];
+	const Outbox &out = sp.ob[cur];
+	const Arrivals A = find_arrivals(in, g, nb, b, lane);
+	const int cnt = sp.count[b];
+	const int T = cnt + A.total;
+	const size_t base = (size_t) b * sp.cap;
+	const size_t obase = (size_t) b * sp.obox;
+	const int tx0 = cx * g.WPC * g.BX, ty0 = by * g.BY;   /* tile origin in cells */
+	const int gby = g.brow0 + by;
+	int oc0 = 0, oc1 = 0, oc2 = 0, oc3 = 0, oc5 = 0, oc6 = 0, oc7 = 0, oc8 = 0;
+	int w = 0;                       /* write cursor of the segment */
+	int bad = 0;
+
+	/* first batch in flight while the tile lands */
+	double nx_ = 0, ny_ = 0, nux = 0, nuy = 0, nuz = 0, nEx = 0, nEy = 0;
+	size_t nsrc = 0;
+	if(lane < T)
+	{
+		const bool own = lane < cnt;
+		nsrc = own ? base + lane : arrival_slot(A, sp, lane - cnt);
+		nx_ = own ? sp.x[nsrc] : in.x[nsrc];
+		ny_ = own ? sp.y[nsrc] : in.y[nsrc];
+		if(MODE != 0)
+		{
+			nux = own ? sp.ux[nsrc] : in.ux[nsrc];
+			nuy = own ? sp.uy[nsrc] : in.uy[nsrc];
+			nuz = own ? sp.uz[nsrc] : in.uz[nsrc];
+		}
+		if(MODE == 1) { nEx = own ? sp.pEx[nsrc] : in.Ex[nsrc]; nEy = own ? sp.pEy[nsrc] : in.Ey[nsrc]; }
+	}
+
 	if(MODE != 1)
 	{
-		if(threadIdx.x == 0)
-		{
-			mbar_init(bar, 1);
-			uint32_t bytes = 2u * (uint32_t) (g.TH * g.TW) * 8u;
-			mbar_expect_tx(bar, bytes);
-			tma_load_2d(tEx, &mapEx, cx * g.WPC * g.BX, by * g.BY, bar);
-			tma_load_2d(tEy, &mapEy, cx * g.WPC * g.BX, by * g.BY, bar);
-		}
 		__syncthreads();
 		if(mbar_wait(bar, 0))
 		{
@@ -288,26 +413,28 @@ k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 		}
 	}
 
-	const int cnt = sp.count[b];
-	const size_t base = (size_t) b * sp.cap;
-	const size_t obase = (size_t) b * sp.ocap;
-	const int tx0 = cx * g.WPC * g.BX, ty0 = by * g.BY;   /* tile origin in cells */
-	const int gby = g.brow0 + by;
-	int nout = 0;
-	int bad = 0;
-
-	for(int i0 = 0; i0 < cnt; i0 += 32)
+	for(int t0 = 0; t0 < T; t0 += 32)
 	{
-		const int i = i0 + lane;
-		const bool valid = i < cnt;
-		const size_t s = base + (valid ? i : 0);
-		double x = 0, y = 0, ux = 0, uy = 0, uz = 0, Ex = 0, Ey = 0;
+		const int t = t0 + lane;
+		const bool valid = t < T;
+		const bool own = t < cnt;
+		const size_t s = nsrc;
+		double x = nx_, y = ny_, ux = nux, uy = nuy, uz = nuz, Ex = nEx, Ey = nEy;
 
-		if(valid)
+		/* prefetch the next batch */
+		if(t + 32 < T)
 		{
-			x = sp.x[s]; y = sp.y[s];
-			if(MODE != 0) { ux = sp.ux[s]; uy = sp.uy[s]; uz = sp.uz[s]; }
-			if(MODE == 1) { Ex = sp.pEx[s]; Ey = sp.pEy[s]; }
+			const bool nown = t + 32 < cnt;
+			nsrc = nown ? base + t + 32 : arrival_slot(A, sp, t + 32 - cnt);
+			nx_ = nown ? sp.x[nsrc] : in.x[nsrc];
+			ny_ = nown ? sp.y[nsrc] : in.y[nsrc];
+			if(MODE != 0)
+			{
+				nux = nown ? sp.ux[nsrc] : in.ux[nsrc];
+				nuy = nown ? sp.uy[nsrc] : in.uy[nsrc];
+				nuz = nown ? sp.uz[nsrc] : in.uz[nsrc];
+			}
+			if(MODE == 1) { nEx = nown ? sp.pEx[nsrc] : in.Ex[nsrc]; nEy = nown ? sp.pEy[nsrc] : in.Ey[nsrc]; }
 		}
 
 		if(MODE != 1 && valid)
@@ -317,7 +444,11 @@ k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 			cic_weights(g, x, y, i0x, i0y, w00, w01, w10, w11);
 			Ex = tile_gather(tEx, g.TW, i0x - tx0, i0y - ty0, w00, w01, w10, w11);
 			Ey = tile_gather(tEy, g.TW, i0x - tx0, i0y - ty0, w00, w01, w10, w11);
-			if(MODE == 0 || sp.pEx) { sp.pEx[s] = Ex; sp.pEy[s] = Ey; }
+			if(MODE == 0)
+			{
+				if(own) { sp.pEx[s] = Ex; sp.pEy[s] = Ey; }
+				else { in.Ex[s] = Ex; in.Ey[s] = Ey; }
+			}
 		}
 
 		if(MODE == 0) continue;
@@ -347,40 +478,66 @@ k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 			}
 		}
 
-		const bool leave = valid && dest != DEST_STAY;
-		if(valid && !leave)
-		{
-			if(pp.set_r) { sp.x[s] = x; sp.y[s] = y; }
-			sp.ux[s] = ux; sp.uy[s] = uy; sp.uz[s] = uz;
-		}
+		const bool stay = valid && dest == DEST_STAY;
+		const bool leave = valid && !stay;
+		const unsigned ms = __ballot_sync(FULL, stay);
+		const int dpos = w + __popc(ms & lt);
+		/* the id (and the kept E) only move when the particle changes slot */
+		const bool moved = !own || dpos != t;
+		long long pid = 0;
+		if(valid && (moved || leave)) pid = own ? sp.id[s] : in.id[s];
+		__syncwarp();                /* every id is read before a neighbour lane may overwrite its slot */
 
-		const unsigned m = __ballot_sync(FULL, leave);
-		if(m)
+		if(stay)
 		{
+			if(dpos < sp.cap)
+			{
+				const size_t d = base + dpos;
+				if(pp.set_r || moved) { sp.x[d] = x; sp.y[d] = y; }
+				sp.ux[d] = ux; sp.uy[d] = uy; sp.uz[d] = uz;
+				if(moved) sp.id[d] = pid;
+				if(sp.pEx) { sp.pEx[d] = Ex; sp.pEy[d] = Ey; }
+			}
+			else bad |= 2;
+		}
+		w += __popc(ms);
+
+		if(ms != __ballot_sync(FULL, valid))
+		{
+			/* rank of every leaver inside its destination region: batches in order,
+			 * lanes in order (one ballot per destination code) */
+			int pos = 0;
+#define RANK(c, cntv) { const unsigned mc = __ballot_sync(FULL, leave && dest == c); \
+	if(dest == c) pos = cntv + __popc(mc & lt); cntv += __popc(mc); }
+			RANK(0, oc0) RANK(1, oc1) RANK(2, oc2) RANK(3, oc3)
+			RANK(5, oc5) RANK(6, oc6) RANK(7, oc7) RANK(8, oc8)
+#undef RANK
 			if(leave)
 			{
-				int pos = nout + __popc(m & ((1u << lane) - 1));
 				if(dest == DEST_FAR) bad |= 4;
-				if(pos < sp.ocap)
+				else if(pos < region_cap(sp, dest))
 				{
-					size_t o = obase + pos;
-					sp.ox[o] = x; sp.oy[o] = y;
-					sp.oux[o] = ux; sp.ouy[o] = uy; sp.ouz[o] = uz;
-					sp.oid[o] = sp.id[s];
-					if(sp.oEx) { sp.oEx[o] = Ex; sp.oEy[o] = Ey; }
-					sp.odest[o] = dest;
-					sp.ohole[o] = i;
+					const size_t o = obase + region_base(sp, dest) + pos;
+					out.x[o] = x; out.y[o] = y;
+					out.ux[o] = ux; out.uy[o] = uy; out.uz[o] = uz;
+					out.id[o] = pid;
+					if(out.Ex) { out.Ex[o] = Ex; out.Ey[o] = Ey; }
 				}
 				else bad |= 2;
-				sp.x[s] = __longlong_as_double(0x7ff8000000000000LL);   /* hole marker */
 			}
-			nout += __popc(m);
 		}
 	}
 
 	if(MODE != 0)
 	{
-		if(lane == 0) sp.ocount[b] = nout < sp.ocap ? nout : sp.ocap;
+		if(lane == 0) sp.count[b] = w < sp.cap ? w : sp.cap;
+		if(lane < 9)
+		{
+			int v = lane == 0 ? oc0 : lane == 1 ? oc1 : lane == 2 ? oc2 : lane == 3 ? oc3 :
+				lane == 5 ? oc5 : lane == 6 ? oc6 : lane == 7 ? oc7 : lane == 8 ? oc8 : 0;
+			const int rc = region_cap(sp, lane);
+			out.count[(size_t) b * 9 + lane] = v < rc ? v : rc;
+		}
 		if(bad)
 		{
 			int bits = 0;
@@ -392,106 +549,57 @@ k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 	}
 }
 
-/* comm_plasma on the device (reference src/comm_plasma.c:1122-1142, X and Y passes in
- * one): (1) the holes left by the leavers are filled with the block's last remaining
- * particles, in order; (2) the particles that the eight neighbour blocks put in their
- * outboxes for this block are appended, neighbours in a fixed order. With several ranks
- * the block rows -1 and nby are ghost outboxes filled from the neighbour ranks.
- * One warp per block; grid = nb / 8 CTAs of 8 warps (blocks need not share a row). */
+/* Appends the pending arrivals of every block (outbox `arr`) to its own segment and
+ * clears the runs it consumed. Not on the per-step path: used before particles are
+ * handed to the host (downloads, diagnostics). One warp per block. */
 __global__ void __launch_bounds__(256)
-k_migrate(SpeciesDev sp, Geom g, int nb, int *__restrict__ errflag)
+k_absorb(SpeciesDev sp, Geom g, int nb, int arr, int *__restrict__ errflag)
 {
 	const int lane = threadIdx.x & 31;
 	const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
 	if(b >= nb) return;
-
+	const Outbox &in = sp.ob[arr];
+	const Arrivals A = find_arrivals(in, g, nb, b, lane);
+	if(A.total == 0) return;
 	const int cnt = sp.count[b];
-	const int no = sp.ocount[b];
 	const size_t base = (size_t) b * sp.cap;
-	const size_t obase = (size_t) b * sp.ocap;
-	int n = cnt - no;                 /* particles that stay */
-
-	/* (1) holes below n are filled from the live slots in [n, cnt) */
-	if(no > 0)
+	if(cnt + A.total > sp.cap)
 	{
-		int filled = 0;               /* next hole to fill = ohole[filled] (ascending) */
-		for(int i0 = n; i0 < cnt; i0 += 32)
-		{
-			const int i = i0 + lane;
-			const bool live = i < cnt && sp.x[base + i] == sp.x[base + i];
-			const unsigned m = __ballot_sync(FULL, live);
-			if(live)
-			{
-				const int k = filled + __popc(m & ((1u << lane) - 1));
-				const size_t d = base + sp.ohole[obase + k];
-				const size_t s = base + i;
-				sp.x[d] = sp.x[s]; sp.y[d] = sp.y[s];
-				sp.ux[d] = sp.ux[s]; sp.uy[d] = sp.uy[s]; sp.uz[d] = sp.uz[s];
-				sp.id[d] = sp.id[s];
-				if(sp.pEx) { sp.pEx[d] = sp.pEx[s]; sp.pEy[d] = sp.pEy[s]; }
-			}
-			filled += __popc(m);
-		}
+		if(lane == 0) atomicOr(errflag, ERRBIT_CAPACITY);
+		return;
 	}
-
-	/* (2) arrivals. Neighbour k sits at (dx, dy) = (k%3-1, k/3-1); what it sends to us
-	 * carries the opposite code 8-k. Ghost block rows hold the other ranks' particles. */
-	const int bx = b % g.nbx, by = b / g.nbx;
-	for(int k = 0; k < 9; k++)
+	for(int f = lane; f < A.total; f += 32)
 	{
-		if(k == DEST_STAY) continue;
-		const int ndx = k % 3 - 1, ndy = k / 3 - 1;
-		int nbx_ = bx + ndx, nby_ = by + ndy;
-		if(nbx_ < 0) nbx_ += g.nbx; else if(nbx_ >= g.nbx) nbx_ -= g.nbx;
-		int src;                       /* index into the outbox arrays */
-		if(g.nby_glob == g.nby)
-		{
-			if(nby_ < 0) nby_ += g.nby; else if(nby_ >= g.nby) nby_ -= g.nby;
-			src = nby_ * g.nbx + nbx_;
-		}
-		else if(nby_ < 0) src = nb + nbx_;                 /* north ghost row */
-		else if(nby_ >= g.nby) src = nb + g.nbx + nbx_;    /* south ghost row */
-		else src = nby_ * g.nbx + nbx_;
-
-		const int want = 8 - k;
-		const int m_ = sp.ocount[src];
-		const size_t sbase = (size_t) src * sp.ocap;
-		for(int j0 = 0; j0 < m_; j0 += 32)
-		{
-			const int j = j0 + lane;
-			const bool hit = j < m_ && sp.odest[sbase + j] == want;
-			const unsigned m = __ballot_sync(FULL, hit);
-			if(hit)
-			{
-				const int pos = n + __popc(m & ((1u << lane) - 1));
-				if(pos < sp.cap)
-				{
-					const size_t d = base + pos, s = sbase + j;
-					sp.x[d] = sp.ox[s]; sp.y[d] = sp.oy[s];
-					sp.ux[d] = sp.oux[s]; sp.uy[d] = sp.ouy[s]; sp.uz[d] = sp.ouz[s];
-					sp.id[d] = sp.oid[s];
-					if(sp.pEx) { sp.pEx[d] = sp.oEx[s]; sp.pEy[d] = sp.oEy[s]; }
-				}
-				else atomicOr(errflag, ERRBIT_CAPACITY);
-			}
-			n += __popc(m);
-		}
+		const size_t so = arrival_slot(A, sp, f), d = base + cnt + f;
+		sp.x[d] = in.x[so]; sp.y[d] = in.y[so];
+		sp.ux[d] = in.ux[so]; sp.uy[d] = in.uy[so]; sp.uz[d] = in.uz[so];
+		sp.id[d] = in.id[so];
+		if(sp.pEx) { sp.pEx[d] = in.Ex[so]; sp.pEy[d] = in.Ey[so]; }
 	}
-	if(lane == 0) sp.count[b] = n < sp.cap ? n : sp.cap;
+	if(lane == 0) sp.count[b] = cnt + A.total;
+	/* the runs are consumed: lane k clears the counter it read */
+	if(lane < 9 && lane != DEST_STAY)
+	{
+		int srck = 0;
+#pragma unroll
+		for(int q = 0; q < 9; q++) if(q == lane) srck = A.src[q];
+		in.count[(size_t) srck * 9 + (8 - lane)] = 0;
+	}
 }
 
 /* interpolate_p2f_rho, reference src/interpolate.c:282-346 / :161-276, accumulate-correct.
- * Each warp sums its block's particles into a private (BY+1) x (BX+1) tile in shared
- * memory: per batch of 32, lanes that share a cell are summed in lane order by the
- * lowest of them (match_any + shuffles), then the four corners are added in four
- * phases; inside a phase distinct cells hit distinct nodes, so plain read-modify-write
- * is race free and the order of every node's sum is fixed. The CTA then merges its WPC
- * tiles left to right and stores: interior nodes to rho (`=` for the first species,
- * `+=` after), bottom row / right column / corner to the halo arrays that
- * k_stitch_* add in a fixed order. rho_reset (src/field.c:163-210) is implicit. */
+ * Each warp sums its block's particles (own segment, then the arrivals in outbox `arr`)
+ * into a private (BY+1) x (BX+1) tile in shared memory. Per batch of 32, lanes that share
+ * a cell are ranked in lane order (match_any); rank r adds in round r, and inside a round
+ * the four corners are added in four phases: within a phase distinct cells hit distinct
+ * nodes, so plain read-modify-write is race free and every node's sum has a fixed order
+ * (batch, rank, corner). The CTA then merges its WPC tiles left to right and stores:
+ * interior nodes to rho (`=` for the first species, `+=` after), bottom row / right
+ * column / corner to the halo arrays that k_stitch_* add in a fixed order. rho_reset
+ * (src/field.c:163-210) is implicit. */
 template <bool FIRST>
 __global__ void __launch_bounds__(32 * MAX_WPC)
-k_deposit(SpeciesDev sp, Geom g, double vq,
+k_deposit(SpeciesDev sp, Geom g, double vq, int nb, int arr,
 		double *__restrict__ rho, double *__restrict__ hb, double *__restrict__ hr,
 		double *__restrict__ hc)
 {
@@ -500,23 +608,41 @@ k_deposit(SpeciesDev sp, Geom g, double vq,
 	const int TWd = g.BX + 1, THd = g.BY + 1, tsz = TWd * THd;
 
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const unsigned lt = (1u << lane) - 1;
 	const int ncx = g.nbx / g.WPC;
 	const int by = blockIdx.x / ncx, cx = blockIdx.x % ncx;
 	const int bx = cx * g.WPC + warp;
 	const int b = by * g.nbx + bx;
 	double *t = tiles + warp * tsz;
 
-	for(int k = lane; k < tsz; k += 32) t[k] = 0.0;
-	__syncwarp();
-
+	const Outbox &in = sp.ob[arr];
+	const Arrivals A = find_arrivals(in, g, nb, b, lane);
 	const int cnt = sp.count[b];
+	const int T = cnt + A.total;
 	const size_t base = (size_t) b * sp.cap;
 	const int cx0 = bx * g.BX, cy0 = by * g.BY;
 
-	for(int i0 = 0; i0 < cnt; i0 += 32)
+	double px = 0, py = 0;
+	if(lane < T)
+	{
+		if(lane < cnt) { px = sp.x[base + lane]; py = sp.y[base + lane]; }
+		else { const size_t so = arrival_slot(A, sp, lane - cnt); px = in.x[so]; py = in.y[so]; }
+	}
+
+	for(int k = lane; k < tsz; k += 32) t[k] = 0.0;
+	__syncwarp();
+
+	for(int i0 = 0; i0 < T; i0 += 32)
 	{
 		const int i = i0 + lane;
-		const bool valid = i < cnt;
+		const bool valid = i < T;
+		const double x = px, y = py;
+		if(i + 32 < T)
+		{
+			if(i + 32 < cnt) { px = sp.x[base + i + 32]; py = sp.y[base + i + 32]; }
+			else { const size_t so = arrival_slot(A, sp, i + 32 - cnt); px = in.x[so]; py = in.y[so]; }
+		}
+
 		int cell = -1 - lane;         /* unique key for idle lanes */
 		int node = 0;
 		double a00 = 0, a01 = 0, a10 = 0, a11 = 0;
@@ -524,35 +650,26 @@ k_deposit(SpeciesDev sp, Geom g, double vq,
 		{
 			int i0x, i0y;
 			double w00, w01, w10, w11;
-			cic_weights(g, sp.x[base + i], sp.y[base + i], i0x, i0y, w00, w01, w10, w11);
+			cic_weights(g, x, y, i0x, i0y, w00, w01, w10, w11);
 			a00 = MUL(w00, vq); a01 = MUL(w01, vq); a10 = MUL(w10, vq); a11 = MUL(w11, vq);
 			node = (i0y - cy0) * TWd + (i0x - cx0);
 			cell = node;
 		}
 		const unsigned peers = __match_any_sync(FULL, cell);
-		const int leader = __ffs(peers) - 1;
-		const int npeers = __popc(peers);
-		const int maxp = __reduce_max_sync(FULL, npeers);
-		/* the leader adds its peers' terms in ascending lane order */
-		for(int j = 1; j < maxp; j++)
+		const int rank = __popc(peers & lt);
+		const int rounds = __reduce_max_sync(FULL, valid ? rank + 1 : 0);
+		for(int r = 0; r < rounds; r++)
 		{
-			int src = lane;
-			if(lane == leader && j < npeers) src = __fns(peers, 0, j + 1);
-			double b00 = __shfl_sync(FULL, a00, src);
-			double b01 = __shfl_sync(FULL, a01, src);
-			double b10 = __shfl_sync(FULL, a10, src);
-			double b11 = __shfl_sync(FULL, a11, src);
-			if(lane == leader && j < npeers) { a00 += b00; a01 += b01; a10 += b10; a11 += b11; }
+			const bool add = valid && rank == r;
+			if(add) t[node] += a00;
+			__syncwarp();
+			if(add) t[node + TWd] += a01;
+			__syncwarp();
+			if(add) t[node + 1] += a10;
+			__syncwarp();
+			if(add) t[node + TWd + 1] += a11;
+			__syncwarp();
 		}
-		const bool add = valid && lane == leader;
-		if(add) t[node] += a00;
-		__syncwarp();
-		if(add) t[node + TWd] += a01;
-		__syncwarp();
-		if(add) t[node + 1] += a10;
-		__syncwarp();
-		if(add) t[node + TWd + 1] += a11;
-		__syncwarp();
 	}
 
 	__syncthreads();
@@ -682,7 +799,7 @@ k_init_uniform(SpeciesDev sp, Geom g, int nb, long long n, long long id0, double
 		sp.uz[base + k] = 0.0;
 		sp.id[base + k] = gid;
 	}
-	if(lane == 0) { sp.count[b] = (int) cnt; sp.ocount[b] = 0; }
+	if(lane == 0) sp.count[b] = (int) cnt;
 }
 
 #endif

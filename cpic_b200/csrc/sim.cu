@@ -49,8 +49,9 @@ struct SpeciesHost {
 	SpeciesDev d;
 	void *block;             /* one allocation: x y ux uy uz id count (the "image") */
 	size_t block_bytes;
-	void *oblock;            /* outboxes */
-	double *pE;              /* optional per-particle E */
+	void *oblock;            /* the two outboxes */
+	double *pE;              /* optional per-particle E (segment and outboxes) */
+	int arr;                 /* outbox that holds the pending arrivals */
 	long long n;
 	double q, m;
 };
@@ -335,25 +336,34 @@ alloc_species(sim_t_ *s, int is, int cap)
 	h.d.count = (int *) (b + 6 * arr);
 	h.d.cap = cap;
 
-	int ocap = ((cap / 2 + 31) / 32) * 32;
-	if(ocap < 64) ocap = 64;
-	h.d.ocap = ocap;
-	const size_t oslot = (size_t) s->nob * ocap;
+	/* outbox regions: four sides of ocs slots, four corners of occ */
+	double frac = s->p.outbox_fraction > 0 ? s->p.outbox_fraction : 0.3;
+	int ocs = (((int) ceil(cap * frac) + 31) / 32) * 32;
+	if(ocs < 32) ocs = 32;
+	int occ = ((ocs / 4 + 31) / 32) * 32;
+	h.d.ocs = ocs;
+	h.d.occ = occ;
+	h.d.obox = 4 * ocs + 4 * occ;
+	const size_t oslot = (size_t) s->nob * h.d.obox;
 	const size_t oarr = align256(oslot * sizeof(double));
-	const size_t oint = align256(oslot * sizeof(int));
-	const size_t ocnt = align256((size_t) s->nob * sizeof(int));
-	CK(cudaMalloc(&h.oblock, 6 * oarr + 2 * oint + ocnt));
-	CK(cudaMemsetAsync(h.oblock, 0, 6 * oarr + 2 * oint + ocnt, s->stream));
-	char *o = (char *) h.oblock;
-	h.d.ox = (double *) (o + 0 * oarr);
-	h.d.oy = (double *) (o + 1 * oarr);
-	h.d.oux = (double *) (o + 2 * oarr);
-	h.d.ouy = (double *) (o + 3 * oarr);
-	h.d.ouz = (double *) (o + 4 * oarr);
-	h.d.oid = (long long *) (o + 5 * oarr);
-	h.d.odest = (int *) (o + 6 * oarr);
-	h.d.ohole = (int *) (o + 6 * oarr + oint);
-	h.d.ocount = (int *) (o + 6 * oarr + 2 * oint);
+	const size_t ocnt = align256((size_t) s->nob * 9 * sizeof(int));
+	const size_t one = 6 * oarr + ocnt;
+	CK(cudaMalloc(&h.oblock, 2 * one));
+	CK(cudaMemsetAsync(h.oblock, 0, 2 * one, s->stream));
+	for(int k = 0; k < 2; k++)
+	{
+		char *o = (char *) h.oblock + k * one;
+		Outbox &ob = h.d.ob[k];
+		ob.x = (double *) (o + 0 * oarr);
+		ob.y = (double *) (o + 1 * oarr);
+		ob.ux = (double *) (o + 2 * oarr);
+		ob.uy = (double *) (o + 3 * oarr);
+		ob.uz = (double *) (o + 4 * oarr);
+		ob.id = (long long *) (o + 5 * oarr);
+		ob.count = (int *) (o + 6 * oarr);
+		ob.Ex = ob.Ey = NULL;
+	}
+	h.arr = 0;
 
 	if(s->p.keep_particle_E) return ensure_particle_E(s, is);
 	return 0;
@@ -365,13 +375,16 @@ ensure_particle_E(sim_t_ *s, int is)
 	SpeciesHost &h = s->sp[is];
 	if(h.d.pEx || !h.block) return 0;
 	const size_t arr = align256((size_t) s->nb * h.d.cap * sizeof(double));
-	const size_t oarr = align256((size_t) s->nob * h.d.ocap * sizeof(double));
-	CK(cudaMalloc(&h.pE, 2 * arr + 2 * oarr));
-	CK(cudaMemsetAsync(h.pE, 0, 2 * arr + 2 * oarr, s->stream));
+	const size_t oarr = align256((size_t) s->nob * h.d.obox * sizeof(double));
+	CK(cudaMalloc(&h.pE, 2 * arr + 4 * oarr));
+	CK(cudaMemsetAsync(h.pE, 0, 2 * arr + 4 * oarr, s->stream));
 	h.d.pEx = h.pE;
 	h.d.pEy = (double *) ((char *) h.pE + arr);
-	h.d.oEx = (double *) ((char *) h.pE + 2 * arr);
-	h.d.oEy = (double *) ((char *) h.pE + 2 * arr + oarr);
+	for(int k = 0; k < 2; k++)
+	{
+		h.d.ob[k].Ex = (double *) ((char *) h.pE + 2 * arr + (2 * k) * oarr);
+		h.d.ob[k].Ey = (double *) ((char *) h.pE + 2 * arr + (2 * k + 1) * oarr);
+	}
 	return 0;
 }
 
@@ -441,7 +454,7 @@ cpic_b200_set_particles(cpic_b200_sim_t *s, int is, int64_t n, const int64_t *id
 	CK(cudaMemcpyAsync(h.d.uz, huz.data(), nslot * sizeof(double), cudaMemcpyHostToDevice, s->stream));
 	CK(cudaMemcpyAsync(h.d.id, hid.data(), nslot * sizeof(long long), cudaMemcpyHostToDevice, s->stream));
 	CK(cudaMemcpyAsync(h.d.count, cnt.data(), (size_t) s->nb * sizeof(int), cudaMemcpyHostToDevice, s->stream));
-	CK(cudaMemsetAsync(h.d.ocount, 0, (size_t) s->nob * sizeof(int), s->stream));
+	for(int k = 0; k < 2; k++) CK(cudaMemsetAsync(h.d.ob[k].count, 0, (size_t) s->nob * 9 * sizeof(int), s->stream));
 	CK(cudaStreamSynchronize(s->stream));
 	h.n = n;
 	return 0;
@@ -462,8 +475,20 @@ cpic_b200_init_uniform(cpic_b200_sim_t *s, int is, int64_t n, int64_t id0, doubl
 	}
 	k_init_uniform<<<(s->nb + 7) / 8, 256, 0, s->stream>>>(h.d, s->g, s->nb, n, id0, vx, vy, seed);
 	CK(cudaGetLastError());
-	CK(cudaMemsetAsync(h.d.ocount, 0, (size_t) s->nob * sizeof(int), s->stream));
+	for(int k = 0; k < 2; k++) CK(cudaMemsetAsync(h.d.ob[k].count, 0, (size_t) s->nob * 9 * sizeof(int), s->stream));
 	h.n = n;
+	return 0;
+}
+
+/* Fold the pending arrivals of one species into the block segments (see k_absorb) */
+static int
+absorb(sim_t_ *s, int is)
+{
+	SpeciesHost &h = s->sp[is];
+	if(!h.block) return 0;
+	k_absorb<<<(s->nb + 7) / 8, 256, 0, s->stream>>>(h.d, s->g, s->nb, h.arr, s->errflag);
+	cudaError_t e = cudaGetLastError();
+	if(e != cudaSuccess) return fail(CPIC_B200_ECUDA, "kernel launch failed: %s", cudaGetErrorString(e));
 	return 0;
 }
 
@@ -474,6 +499,7 @@ cpic_b200_num_particles(cpic_b200_sim_t *s, int is)
 	SpeciesHost &h = s->sp[is];
 	if(!h.block) return 0;
 	cudaSetDevice(s->device);
+	if(absorb(s, is)) return -1;
 	std::vector<int> cnt((size_t) s->nb);
 	if(cudaMemcpyAsync(cnt.data(), h.d.count, cnt.size() * sizeof(int), cudaMemcpyDeviceToHost, s->stream) != cudaSuccess) return -1;
 	if(cudaStreamSynchronize(s->stream) != cudaSuccess) return -1;
@@ -490,6 +516,7 @@ cpic_b200_get_particles(cpic_b200_sim_t *s, int is, int64_t capn, int64_t *id, d
 	SpeciesHost &h = s->sp[is];
 	if(!h.block) return 0;
 	cudaSetDevice(s->device);
+	if(absorb(s, is)) return -1;
 	const int cap = h.d.cap;
 	std::vector<int> cnt((size_t) s->nb);
 	if(cudaMemcpyAsync(cnt.data(), h.d.count, cnt.size() * sizeof(int), cudaMemcpyDeviceToHost, s->stream) != cudaSuccess
@@ -658,8 +685,11 @@ launch_gather_push(sim_t_ *s, int is)
 		attr_set[MODE] = true;
 	}
 	const int ctas = s->nb / g.WPC;
+	/* a push reads the pending arrivals and fills the other outbox */
+	const int cur = MODE == 0 ? h.arr : h.arr ^ 1;
 	k_gather_push<MODE><<<ctas, 32 * g.WPC, s->smem_push, s->stream>>>(h.d, g, push_params(s, is),
-			s->mapEx, s->mapEy, s->errflag);
+			s->mapEx, s->mapEy, s->nb, cur, s->errflag);
+	if(MODE != 0) h.arr = cur;
 	return check_launch(s);
 }
 
@@ -679,22 +709,21 @@ cpic_b200_stage_plasma_E(cpic_b200_sim_t *s)
 	return 0;
 }
 
-/* comm_plasma, reference src/comm_plasma.c:1122-1142 */
+/* comm_plasma, reference src/comm_plasma.c:1122-1142. Inside one rank the exchange is
+ * part of the push kernel (leavers go straight to the outbox region their new block
+ * reads); what is left is the Y pass between ranks (src/comm_plasma.c:1086-1120): the
+ * regions of the edge block rows that point across the slab face travel to the
+ * neighbour's ghost outbox rows. */
 static int
 exchange(sim_t_ *s)
 {
+	if(!s->comm) return 0;
 	StageTimer t(s, T_EXCHANGE);
 	for(int is = 0; is < s->p.nspecies; is++)
 	{
 		SpeciesHost &h = s->sp[is];
 		if(!h.block) continue;
-		if(s->comm)
-		{
-			int rc = comm_particles(s->comm, &h.d, s->g, s->nb, s->stream, s->errflag, &s->launches);
-			if(rc) return rc;
-		}
-		k_migrate<<<(s->nb + 7) / 8, 256, 0, s->stream>>>(h.d, s->g, s->nb, s->errflag);
-		int rc = check_launch(s);
+		int rc = comm_particles(s->comm, &h.d, h.arr, s->g, s->nb, s->stream, s->errflag, &s->launches);
 		if(rc) return rc;
 	}
 	return 0;
@@ -715,8 +744,6 @@ stage_plasma_r(sim_t_ *s)
 			if(rc) return rc;
 		}
 	}
-	/* at iteration 0 nothing moves (src/mover.c:204-215), the exchange is a no-op */
-	if(s->iter == 0) return 0;
 	return exchange(s);
 }
 
@@ -749,8 +776,8 @@ cpic_b200_stage_field_rho(cpic_b200_sim_t *s)
 		SpeciesHost &h = s->sp[is];
 		if(!h.block) continue;
 		const double vq = -h.q / s->p.e0;       /* reference src/interpolate.c:307 */
-		if(first) k_deposit<true><<<ctas, 32 * g.WPC, s->smem_dep, s->stream>>>(h.d, g, vq, s->rho, s->hb, s->hr, s->hc);
-		else k_deposit<false><<<ctas, 32 * g.WPC, s->smem_dep, s->stream>>>(h.d, g, vq, s->rho, s->hb, s->hr, s->hc);
+		if(first) k_deposit<true><<<ctas, 32 * g.WPC, s->smem_dep, s->stream>>>(h.d, g, vq, s->nb, h.arr, s->rho, s->hb, s->hr, s->hc);
+		else k_deposit<false><<<ctas, 32 * g.WPC, s->smem_dep, s->stream>>>(h.d, g, vq, s->nb, h.arr, s->rho, s->hb, s->hr, s->hc);
 		first = false;
 		int rc = check_launch(s);
 		if(rc) return rc;
@@ -948,6 +975,7 @@ cpic_b200_energy(cpic_b200_sim_t *s, double *kinetic, double *potential)
 	{
 		SpeciesHost &h = s->sp[is];
 		if(!h.block) continue;
+		if(absorb(s, is)) return CPIC_B200_ECUDA;
 		k_kinetic<<<(s->nb + 7) / 8, 256, 0, s->stream>>>(h.d, s->nb, s->red);
 		k_sum<<<1, 1024, 0, s->stream>>>(s->red, s->nb, res);
 		CK(cudaMemcpyAsync(&v, res, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
@@ -985,6 +1013,7 @@ cpic_b200_image_download(cpic_b200_sim_t *s, void *host, int64_t bytes)
 	{
 		SpeciesHost &h = s->sp[is];
 		if(!h.block) continue;
+		if(absorb(s, is)) return CPIC_B200_ECUDA;
 		CK(cudaMemcpyAsync(p, h.block, h.block_bytes, cudaMemcpyDeviceToHost, s->stream));
 		p += h.block_bytes;
 	}
@@ -1002,6 +1031,8 @@ cpic_b200_image_upload(cpic_b200_sim_t *s, const void *host, int64_t bytes)
 	{
 		SpeciesHost &h = s->sp[is];
 		if(!h.block) continue;
+		/* the image holds every particle in the segments: no arrivals are pending */
+		for(int k = 0; k < 2; k++) CK(cudaMemsetAsync(h.d.ob[k].count, 0, (size_t) s->nob * 9 * sizeof(int), s->stream));
 		CK(cudaMemcpyAsync(h.block, p, h.block_bytes, cudaMemcpyHostToDevice, s->stream));
 		p += h.block_bytes;
 	}

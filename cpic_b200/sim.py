@@ -29,6 +29,7 @@ class Params:
     device: int = -1
     capacity_factor: float = 0.0
     keep_particle_E: bool = False
+    outbox_fraction: float = 0.0
 
     def to_c(self):
         p = ParamsC()
@@ -42,13 +43,15 @@ class Params:
         p.rank, p.nranks, p.device = self.rank, self.nranks, self.device
         p.capacity_factor = self.capacity_factor
         p.keep_particle_E = int(self.keep_particle_E)
+        p.outbox_fraction = self.outbox_fraction
         return p
 
     @staticmethod
     def from_c(p):
         n = p.nspecies
         return Params(p.nx, p.ny, p.Lx, p.Ly, p.dt, p.e0, tuple(p.B), tuple(p.q[:n]), tuple(p.m[:n]),
-                      p.plasma_chunks, p.rank, p.nranks, p.device, p.capacity_factor, bool(p.keep_particle_E))
+                      p.plasma_chunks, p.rank, p.nranks, p.device, p.capacity_factor, bool(p.keep_particle_E),
+                      p.outbox_fraction)
 
 
 @dataclass

@@ -59,6 +59,8 @@ typedef struct cpic_b200_params {
 	int32_t device;             /* CUDA device ordinal, -1 = current */
 	double capacity_factor;     /* particle-block slack over the fullest block, 0 = default (1.5) */
 	int32_t keep_particle_E;    /* 1: stage_plasma_r also keeps the gathered E per particle */
+	double outbox_fraction;     /* exchange buffer per block side as a share of the block capacity,
+	                             * 0 = default (0.5); corners get a quarter of it */
 } cpic_b200_params_t;
 
 typedef struct cpic_b200_sim cpic_b200_sim_t;
