@@ -45,7 +45,8 @@ struct Geom {
 	int row0;            /* first global row of the slab = rank * ny */
 	int S;               /* row stride of rho and phi: 2*(nx/2+1) (reference src/solver.c:381-433) */
 	int SE;              /* row stride of the device E arrays: nx + wrap columns, even */
-	int BX, BY;          /* cells per particle block */
+	int BX, BY;          /* cells per particle block (powers of two) */
+	int lBX, lBY;        /* their base-2 logarithms */
 	int nbx, nby;        /* blocks per slab row / column */
 	int nby_glob;        /* nby * nranks */
 	int brow0;           /* first global block row = rank * nby */
@@ -76,12 +77,40 @@ cell_floor_y(const Geom &g, double y)
 	return fmin(fmax(bs, 0.0), (double) (g.ny - 1));
 }
 
+/* Integer forms: floor through one round-down conversion, clamped in integer registers.
+ * Same cells as the double forms above for every position inside the domain. */
+HD int
+cell_ix(const Geom &g, double x)
+{
+#ifdef __CUDA_ARCH__
+	int c = __double2int_rd(MUL(x, g.idx));
+#else
+	int c = (int) floor(x * g.idx);
+#endif
+	return c < 0 ? 0 : (c > g.nx - 1 ? g.nx - 1 : c);
+}
+
+HD int
+cell_iy(const Geom &g, double y)
+{
+#ifdef __CUDA_ARCH__
+	int c = __double2int_rd(MUL(SUB(y, g.y0), g.idy));
+#else
+	int c = (int) floor((y - g.y0) * g.idy);
+#endif
+	return c < 0 ? 0 : (c > g.ny - 1 ? g.ny - 1 : c);
+}
+
 /* Global row of a position (for the exchange between slabs) */
 HD int
 global_row(const Geom &g, double y)
 {
-	double bs = floor(MUL(y, g.idy));
-	return (int) fmin(fmax(bs, 0.0), (double) (g.ny_glob - 1));
+#ifdef __CUDA_ARCH__
+	int c = __double2int_rd(MUL(y, g.idy));
+#else
+	int c = (int) floor(y * g.idy);
+#endif
+	return c < 0 ? 0 : (c > g.ny_glob - 1 ? g.ny_glob - 1 : c);
 }
 
 /* Bilinear (CIC) weights, restating reference src/interpolate.c:77-100 (weights),
@@ -94,13 +123,13 @@ cic_weights(const Geom &g, double x, double y, int &i0x, int &i0y,
 	double bd, bs, relx, rely, delx, dely;
 
 	bd = x;
-	bs = cell_floor_x(g, x);
-	i0x = (int) bs;
+	i0x = cell_ix(g, x);
+	bs = (double) i0x;
 	relx = MUL(SUB(bd, MUL(bs, g.dx)), g.idx);
 
 	bd = SUB(y, g.y0);
-	bs = cell_floor_y(g, y);
-	i0y = (int) bs;
+	i0y = cell_iy(g, y);
+	bs = (double) i0y;
 	rely = MUL(SUB(bd, MUL(bs, g.dx)), g.idy);
 
 	delx = SUB(1.0, relx);
@@ -115,9 +144,9 @@ cic_weights(const Geom &g, double x, double y, int &i0x, int &i0y,
 HD int
 block_of(const Geom &g, double x, double y)
 {
-	int cx = (int) cell_floor_x(g, x);
-	int cy = (int) cell_floor_y(g, y);
-	return (cy / g.BY) * g.nbx + cx / g.BX;
+	int cx = cell_ix(g, x);
+	int cy = cell_iy(g, y);
+	return (cy >> g.lBY) * g.nbx + (cx >> g.lBX);
 }
 
 /* Shortest signed distance between two indices on a ring of n */

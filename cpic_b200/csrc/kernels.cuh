@@ -121,6 +121,26 @@ tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar)
 			: "memory");
 }
 
+/* 8-byte asynchronous global->shared copy (LDGSTS): the particle pipeline's prefetch */
+__device__ __forceinline__ void
+cp_async8(void *dst, const void *src)
+{
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(smem_u32(dst)), "l"(src) : "memory");
+}
+
+__device__ __forceinline__ void
+cp_async_commit()
+{
+	asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+template <int N>
+__device__ __forceinline__ void
+cp_async_wait()
+{
+	asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory");
+}
+
 /* ------------------------------------------------------------ field kernels */
 
 /* MFT_kernel, reference src/solver.c:337-363: g[l][k] *= G[l][k]. 16 B per element
@@ -240,17 +260,31 @@ k_rho_fold(double *__restrict__ rho, const double *__restrict__ recv, Geom g)
 __device__ __forceinline__ void
 boris(const PushParams &pp, double Ex, double Ey, double &ux, double &uy, double &uz)
 {
-	/* reference src/mover.c:22-70; per-component s denominator as in the reference */
+	/* reference src/mover.c:22-70; per-component s denominator as in the reference.
+	 * t and s depend on the species only (B is uniform): formed once on the host. */
 	const double k = pp.dtqm2;
-	/* t and s depend on the species only (B is uniform): formed once on the host */
 	const double tx = pp.tx, ty = pp.ty, tz = pp.tz, sx = pp.sx, sy = pp.sy, sz = pp.sz;
 	const double mx = FMA(k, Ex, ux), my = FMA(k, Ey, uy), mz = uz;      /* E_z = 0 */
-	const double px = ADD(SUB(MUL(my, tz), MUL(mz, ty)), mx);
-	const double py = ADD(SUB(MUL(mz, tx), MUL(mx, tz)), my);
-	const double pz = ADD(SUB(MUL(mx, ty), MUL(my, tx)), mz);
-	const double qx = ADD(SUB(MUL(py, sz), MUL(pz, sy)), mx);
-	const double qy = ADD(SUB(MUL(pz, sx), MUL(px, sz)), my);
-	const double qz = ADD(SUB(MUL(px, sy), MUL(py, sx)), mz);
+	double qx, qy, qz;
+	if(tx == 0.0 && ty == 0.0)
+	{
+		/* B along Z (every shipped configuration): the products with t_x, t_y, s_x, s_y
+		 * are exact zeros, so dropping them leaves every bit as in the general branch */
+		const double px = ADD(MUL(my, tz), mx);
+		const double py = ADD(-MUL(mx, tz), my);
+		qx = ADD(MUL(py, sz), mx);
+		qy = ADD(-MUL(px, sz), my);
+		qz = mz;
+	}
+	else
+	{
+		const double px = ADD(SUB(MUL(my, tz), MUL(mz, ty)), mx);
+		const double py = ADD(SUB(MUL(mz, tx), MUL(mx, tz)), my);
+		const double pz = ADD(SUB(MUL(mx, ty), MUL(my, tx)), mz);
+		qx = ADD(SUB(MUL(py, sz), MUL(pz, sy)), mx);
+		qy = ADD(SUB(MUL(pz, sx), MUL(px, sz)), my);
+		qz = ADD(SUB(MUL(px, sy), MUL(py, sx)), mz);
+	}
 	ux = FMA(k, Ex, qx);
 	uy = FMA(k, Ey, qy);
 	uz = qz;
@@ -271,16 +305,17 @@ tile_gather(const double *t, int TW, int lx, int ly, double w00, double w01, dou
 
 /* The arrivals of block b: lane k < 9 (k != 4) looks at neighbour k, which sits at
  * (k%3-1, k/3-1) and addressed b with code 8-k. With several ranks the block rows -1 and
- * nby are ghost outboxes filled from the neighbour ranks. Returns the total; every lane
- * gets the nine run starts (exclusive prefix) and source blocks in registers. */
+ * nby are ghost outboxes filled from the neighbour ranks. The nine run starts (exclusive
+ * prefix) and source blocks go to the warp's scratch in shared memory (18 ints);
+ * returns the total. */
 struct Arrivals {
-	int start[9];
-	int src[9];
+	const int *start;        /* [9] */
+	const int *src;          /* [9] */
 	int total;
 };
 
 __device__ __forceinline__ Arrivals
-find_arrivals(const Outbox &in, const Geom &g, int nb, int b, int lane)
+find_arrivals(const Outbox &in, const Geom &g, int nb, int b, int lane, int *scratch)
 {
 	const int bx = b % g.nbx, by = b / g.nbx;
 	int src = 0, a_k = 0;
@@ -307,13 +342,10 @@ find_arrivals(const Outbox &in, const Geom &g, int nb, int b, int lane)
 	}
 	Arrivals A;
 	A.total = __shfl_sync(FULL, apre, 8);
-	apre -= a_k;
-#pragma unroll
-	for(int k = 0; k < 9; k++)
-	{
-		A.start[k] = __shfl_sync(FULL, apre, k);
-		A.src[k] = __shfl_sync(FULL, src, k);
-	}
+	if(lane < 9) { scratch[lane] = apre - a_k; scratch[9 + lane] = src; }
+	__syncwarp();
+	A.start = scratch;
+	A.src = scratch + 9;
 	return A;
 }
 
@@ -324,10 +356,7 @@ arrival_slot(const Arrivals &A, const SpeciesDev &sp, int f)
 	int k = 0;
 #pragma unroll
 	for(int q = 1; q < 9; q++) if(f >= A.start[q]) k = q;
-	int sb = 0, st = 0;
-#pragma unroll
-	for(int q = 0; q < 9; q++) if(q == k) { sb = A.src[q]; st = A.start[q]; }
-	return (size_t) sb * sp.obox + region_base(sp, 8 - k) + (f - st);
+	return (size_t) A.src[k] * sp.obox + region_base(sp, 8 - k) + (f - A.start[k]);
 }
 
 /* MODE 0: stage_plasma_E alone   (gather, store E per particle)
@@ -343,16 +372,25 @@ arrival_slot(const Arrivals &A, const SpeciesDev &sp, int f)
  * position); one that leaves goes to the region of its destination in outbox `cur`.
  * Ranks inside a batch come from ballots, so the order is: batches in order, lanes in
  * order. MODE 0 moves nothing. */
+#define PIPE_STAGES 3
+
+/* arrays staged per batch: x y (ux uy uz id) (Ex Ey) */
+template <int MODE> struct PipeArrays { static const int N = MODE == 0 ? 2 : MODE == 2 ? 6 : 8; };
+
 template <int MODE>
-__global__ void __launch_bounds__(32 * MAX_WPC, 3)
+__global__ void __launch_bounds__(32 * MAX_WPC, 4)
 k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 		const __grid_constant__ CUtensorMap mapEx, const __grid_constant__ CUtensorMap mapEy,
 		int nb, int cur, int *__restrict__ errflag)
 {
+	constexpr int NARR = PipeArrays<MODE>::N;
 	extern __shared__ __align__(128) unsigned char smem[];
 	uint64_t *bar = (uint64_t *) smem;
-	double *tEx = (double *) (smem + 128);
+	int *wscratch = (int *) (smem + 128) + (threadIdx.x >> 5) * 32;   /* 32 ints per warp */
+	double *tEx = (double *) (smem + 128 + MAX_WPC * 32 * sizeof(int));
 	double *tEy = tEx + g.tile_dbl;
+	/* per-warp ring of PIPE_STAGES batches x NARR arrays x 32 lanes */
+	double *ring = tEy + g.tile_dbl + (threadIdx.x >> 5) * (PIPE_STAGES * NARR * 32);
 
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const unsigned lt = (1u << lane) - 1;
@@ -360,6 +398,8 @@ k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 	const int by = blockIdx.x / ncx, cx = blockIdx.x % ncx;
 	const int bx = cx * g.WPC + warp;
 	const int b = by * g.nbx + bx;
+	int *ocnt = wscratch + 18;       /* leavers per destination code so far */
+	if(lane < 9) ocnt[lane] = 0;
 
 	if(MODE != 1 && threadIdx.x == 0)
 	{
@@ -374,33 +414,50 @@ k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 	 * previous push's outbox and fills `cur` */
 	const Outbox &in = sp.ob[MODE == 0 ? cur : cur ^ 1];
 	const Outbox &out = sp.ob[cur];
-	const Arrivals A = find_arrivals(in, g, nb, b, lane);
+	const Arrivals A = find_arrivals(in, g, nb, b, lane, wscratch);
 	const int cnt = sp.count[b];
-	const int T = cnt + A.total;
-	const size_t base = (size_t) b * sp.cap;
-	const size_t obase = (size_t) b * sp.obox;
+	const unsigned base = (unsigned) b * (unsigned) sp.cap;      /* slot indices fit 32 bits (checked on the host) */
+	const unsigned obase = (unsigned) b * (unsigned) sp.obox;
 	const int tx0 = cx * g.WPC * g.BX, ty0 = by * g.BY;   /* tile origin in cells */
 	const int gby = g.brow0 + by;
-	int oc0 = 0, oc1 = 0, oc2 = 0, oc3 = 0, oc5 = 0, oc6 = 0, oc7 = 0, oc8 = 0;
+	/* the walk: nbo batches over the own segment, then nba over the arrivals */
+	const int nbo = (cnt + 31) >> 5, nba = (A.total + 31) >> 5, nbt = nbo + nba;
 	int w = 0;                       /* write cursor of the segment */
 	int bad = 0;
+	unsigned idmask = 0;             /* bit (bi % PIPE_STAGES): the ids of that staged batch were fetched */
 
-	/* first batch in flight while the tile lands */
-	double nx_ = 0, ny_ = 0, nux = 0, nuy = 0, nuz = 0, nEx = 0, nEy = 0;
-	size_t nsrc = 0;
-	if(lane < T)
+	/* Stage batch bi: every lane copies its own element of every array into the ring
+	 * (asynchronously, no registers held); with_id also fetches the ids. Returns the
+	 * lane's source slot through the ring itself (array slot NARR-1 reused as index for
+	 * MODE 0 is not needed: the slot is recomputed). */
+#define ISSUE_BATCH(bi, with_id) do { \
+	const bool own_ = (bi) < nbo; \
+	const int t_ = (own_ ? (bi) : (bi) - nbo) * 32 + lane; \
+	double *st_ = ring + ((bi) % PIPE_STAGES) * (NARR * 32) + lane; \
+	if(with_id) idmask |= 1u << ((bi) % PIPE_STAGES); else idmask &= ~(1u << ((bi) % PIPE_STAGES)); \
+	if(t_ < (own_ ? cnt : A.total)) { \
+		if(own_) { \
+			const unsigned q_ = base + t_; \
+			cp_async8(st_ + 0 * 32, sp.x + q_); cp_async8(st_ + 1 * 32, sp.y + q_); \
+			if(MODE != 0) { cp_async8(st_ + 2 * 32, sp.ux + q_); cp_async8(st_ + 3 * 32, sp.uy + q_); \
+				cp_async8(st_ + 4 * 32, sp.uz + q_); if(with_id) cp_async8(st_ + 5 * 32, sp.id + q_); } \
+			if(MODE == 1) { cp_async8(st_ + 6 * 32, sp.pEx + q_); cp_async8(st_ + 7 * 32, sp.pEy + q_); } \
+		} else { \
+			const unsigned q_ = (unsigned) arrival_slot(A, sp, t_); \
+			cp_async8(st_ + 0 * 32, in.x + q_); cp_async8(st_ + 1 * 32, in.y + q_); \
+			if(MODE != 0) { cp_async8(st_ + 2 * 32, in.ux + q_); cp_async8(st_ + 3 * 32, in.uy + q_); \
+				cp_async8(st_ + 4 * 32, in.uz + q_); if(with_id) cp_async8(st_ + 5 * 32, in.id + q_); } \
+			if(MODE == 1) { cp_async8(st_ + 6 * 32, in.Ex + q_); cp_async8(st_ + 7 * 32, in.Ey + q_); } \
+		} \
+	} \
+	cp_async_commit(); } while(0)
+
+	/* prologue: PIPE_STAGES-1 batches in flight while the tile lands */
+#pragma unroll
+	for(int k = 0; k < PIPE_STAGES - 1; k++)
 	{
-		const bool own = lane < cnt;
-		nsrc = own ? base + lane : arrival_slot(A, sp, lane - cnt);
-		nx_ = own ? sp.x[nsrc] : in.x[nsrc];
-		ny_ = own ? sp.y[nsrc] : in.y[nsrc];
-		if(MODE != 0)
-		{
-			nux = own ? sp.ux[nsrc] : in.ux[nsrc];
-			nuy = own ? sp.uy[nsrc] : in.uy[nsrc];
-			nuz = own ? sp.uz[nsrc] : in.uz[nsrc];
-		}
-		if(MODE == 1) { nEx = own ? sp.pEx[nsrc] : in.Ex[nsrc]; nEy = own ? sp.pEy[nsrc] : in.Ey[nsrc]; }
+		if(k < nbt) ISSUE_BATCH(k, k >= nbo);
+		else cp_async_commit();
 	}
 
 	if(MODE != 1)
@@ -409,32 +466,38 @@ k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 		if(mbar_wait(bar, 0))
 		{
 			if(threadIdx.x == 0) atomicOr(errflag, ERRBIT_TMA);
+			cp_async_wait<0>();
 			return;
 		}
 	}
 
-	for(int t0 = 0; t0 < T; t0 += 32)
+	for(int bi = 0; bi < nbt; bi++)
 	{
-		const int t = t0 + lane;
-		const bool valid = t < T;
-		const bool own = t < cnt;
-		const size_t s = nsrc;
-		double x = nx_, y = ny_, ux = nux, uy = nuy, uz = nuz, Ex = nEx, Ey = nEy;
+		const bool own = bi < nbo;                       /* warp-uniform */
+		const int t = (own ? bi : bi - nbo) * 32 + lane; /* index inside the segment / the arrivals */
+		const bool valid = t < (own ? cnt : A.total);
 
-		/* prefetch the next batch */
-		if(t + 32 < T)
+		/* keep the pipeline full: batch bi + PIPE_STAGES - 1. The ids are needed only by
+		 * particles that change slot: every arrival, and segment particles once the write
+		 * cursor lags the read position (a late fetch covers the batch where that starts). */
 		{
-			const bool nown = t + 32 < cnt;
-			nsrc = nown ? base + t + 32 : arrival_slot(A, sp, t + 32 - cnt);
-			nx_ = nown ? sp.x[nsrc] : in.x[nsrc];
-			ny_ = nown ? sp.y[nsrc] : in.y[nsrc];
-			if(MODE != 0)
-			{
-				nux = nown ? sp.ux[nsrc] : in.ux[nsrc];
-				nuy = nown ? sp.uy[nsrc] : in.uy[nsrc];
-				nuz = nown ? sp.uz[nsrc] : in.uz[nsrc];
-			}
-			if(MODE == 1) { nEx = nown ? sp.pEx[nsrc] : in.Ex[nsrc]; nEy = nown ? sp.pEy[nsrc] : in.Ey[nsrc]; }
+			const int bn = bi + PIPE_STAGES - 1;
+			if(bn < nbt) ISSUE_BATCH(bn, bn >= nbo || w != bi * 32);
+			else cp_async_commit();
+		}
+		cp_async_wait<PIPE_STAGES - 1>();                /* batch bi has landed (own copies) */
+
+		const double *st = ring + (bi % PIPE_STAGES) * (NARR * 32) + lane;
+		const bool have_id = (idmask >> (bi % PIPE_STAGES)) & 1;
+		/* source slot: needed for the E store of MODE 0 and the late id fetch (segment only) */
+		const unsigned s = own ? base + t : ((MODE == 0 && valid) ? (unsigned) arrival_slot(A, sp, t) : 0u);
+		double x = 0, y = 0, ux = 0, uy = 0, uz = 0, Ex = 0, Ey = 0;
+		long long pid = 0;
+		if(valid)
+		{
+			x = st[0 * 32]; y = st[1 * 32];
+			if(MODE != 0) { ux = st[2 * 32]; uy = st[3 * 32]; uz = st[4 * 32]; if(have_id) pid = __double_as_longlong(st[5 * 32]); }
+			if(MODE == 1) { Ex = st[6 * 32]; Ey = st[7 * 32]; }
 		}
 
 		if(MODE != 1 && valid)
@@ -469,12 +532,15 @@ k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 				if(x >= g.Lx) x = SUB(x, g.Lx); else if(x < 0.0) x = ADD(x, g.Lx);
 				if(y >= g.Ly) y = SUB(y, g.Ly); else if(y < 0.0) y = ADD(y, g.Ly);
 
-				int ncxb = (int) cell_floor_x(g, x) / g.BX;
-				int ngby = global_row(g, y) / g.BY;
-				int ddx = ring_delta(ncxb, bx, g.nbx);
-				int ddy = ring_delta(ngby, gby, g.nby_glob);
-				if(ddx < -1 || ddx > 1 || ddy < -1 || ddy > 1) dest = DEST_FAR;
-				else dest = (ddy + 1) * 3 + (ddx + 1);
+				const int ncxb = cell_ix(g, x) >> g.lBX;
+				const int ngby = global_row(g, y) >> g.lBY;
+				if(ncxb != bx || ngby != gby)
+				{
+					const int ddx = ring_delta(ncxb, bx, g.nbx);
+					const int ddy = ring_delta(ngby, gby, g.nby_glob);
+					if(ddx < -1 || ddx > 1 || ddy < -1 || ddy > 1) dest = DEST_FAR;
+					else dest = (ddy + 1) * 3 + (ddx + 1);
+				}
 			}
 		}
 
@@ -484,15 +550,14 @@ k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 		const int dpos = w + __popc(ms & lt);
 		/* the id (and the kept E) only move when the particle changes slot */
 		const bool moved = !own || dpos != t;
-		long long pid = 0;
-		if(valid && (moved || leave)) pid = own ? sp.id[s] : in.id[s];
+		if(!have_id && valid && (moved || leave)) pid = sp.id[s];      /* late fetch: first shifted batch only */
 		__syncwarp();                /* every id is read before a neighbour lane may overwrite its slot */
 
 		if(stay)
 		{
 			if(dpos < sp.cap)
 			{
-				const size_t d = base + dpos;
+				const unsigned d = base + dpos;
 				if(pp.set_r || moved) { sp.x[d] = x; sp.y[d] = y; }
 				sp.ux[d] = ux; sp.uy[d] = uy; sp.uz[d] = uz;
 				if(moved) sp.id[d] = pid;
@@ -502,22 +567,20 @@ k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 		}
 		w += __popc(ms);
 
-		if(ms != __ballot_sync(FULL, valid))
+		const unsigned ml = __ballot_sync(FULL, leave);
+		if(ml)
 		{
-			/* rank of every leaver inside its destination region: batches in order,
-			 * lanes in order (one ballot per destination code) */
-			int pos = 0;
-#define RANK(c, cntv) { const unsigned mc = __ballot_sync(FULL, leave && dest == c); \
-	if(dest == c) pos = cntv + __popc(mc & lt); cntv += __popc(mc); }
-			RANK(0, oc0) RANK(1, oc1) RANK(2, oc2) RANK(3, oc3)
-			RANK(5, oc5) RANK(6, oc6) RANK(7, oc7) RANK(8, oc8)
-#undef RANK
 			if(leave)
 			{
+				/* rank inside the destination region: batches in order, lanes in order */
+				const unsigned peers = __match_any_sync(ml, dest);
+				const int pos = ocnt[dest] + __popc(peers & lt);
+				__syncwarp(ml);
+				if((peers & lt) == 0) ocnt[dest] = pos + __popc(peers);
 				if(dest == DEST_FAR) bad |= 4;
 				else if(pos < region_cap(sp, dest))
 				{
-					const size_t o = obase + region_base(sp, dest) + pos;
+					const unsigned o = obase + region_base(sp, dest) + pos;
 					out.x[o] = x; out.y[o] = y;
 					out.ux[o] = ux; out.uy[o] = uy; out.uz[o] = uz;
 					out.id[o] = pid;
@@ -525,16 +588,18 @@ k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 				}
 				else bad |= 2;
 			}
+			__syncwarp();
 		}
 	}
+#undef ISSUE_BATCH
+	cp_async_wait<0>();
 
 	if(MODE != 0)
 	{
 		if(lane == 0) sp.count[b] = w < sp.cap ? w : sp.cap;
 		if(lane < 9)
 		{
-			int v = lane == 0 ? oc0 : lane == 1 ? oc1 : lane == 2 ? oc2 : lane == 3 ? oc3 :
-				lane == 5 ? oc5 : lane == 6 ? oc6 : lane == 7 ? oc7 : lane == 8 ? oc8 : 0;
+			const int v = ocnt[lane];
 			const int rc = region_cap(sp, lane);
 			out.count[(size_t) b * 9 + lane] = v < rc ? v : rc;
 		}
@@ -558,8 +623,9 @@ k_absorb(SpeciesDev sp, Geom g, int nb, int arr, int *__restrict__ errflag)
 	const int lane = threadIdx.x & 31;
 	const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
 	if(b >= nb) return;
+	__shared__ int scratch[8][18];
 	const Outbox &in = sp.ob[arr];
-	const Arrivals A = find_arrivals(in, g, nb, b, lane);
+	const Arrivals A = find_arrivals(in, g, nb, b, lane, scratch[threadIdx.x >> 5]);
 	if(A.total == 0) return;
 	const int cnt = sp.count[b];
 	const size_t base = (size_t) b * sp.cap;
@@ -580,10 +646,7 @@ k_absorb(SpeciesDev sp, Geom g, int nb, int arr, int *__restrict__ errflag)
 	/* the runs are consumed: lane k clears the counter it read */
 	if(lane < 9 && lane != DEST_STAY)
 	{
-		int srck = 0;
-#pragma unroll
-		for(int q = 0; q < 9; q++) if(q == lane) srck = A.src[q];
-		in.count[(size_t) srck * 9 + (8 - lane)] = 0;
+		in.count[(size_t) A.src[lane] * 9 + (8 - lane)] = 0;
 	}
 }
 
@@ -615,8 +678,9 @@ k_deposit(SpeciesDev sp, Geom g, double vq, int nb, int arr,
 	const int b = by * g.nbx + bx;
 	double *t = tiles + warp * tsz;
 
+	__shared__ int scratch[MAX_WPC][18];
 	const Outbox &in = sp.ob[arr];
-	const Arrivals A = find_arrivals(in, g, nb, b, lane);
+	const Arrivals A = find_arrivals(in, g, nb, b, lane, scratch[warp]);
 	const int cnt = sp.count[b];
 	const int T = cnt + A.total;
 	const size_t base = (size_t) b * sp.cap;

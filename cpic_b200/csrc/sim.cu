@@ -182,6 +182,8 @@ cpic_b200_create(const cpic_b200_params_t *pp, cpic_b200_sim_t **out)
 	g.S = 2 * (g.nx / 2 + 1);
 	g.BX = pick_div(g.nx, 8);
 	g.BY = pick_div(g.ny, 8);
+	g.lBX = g.BX == 8 ? 3 : g.BX == 4 ? 2 : g.BX == 2 ? 1 : 0;
+	g.lBY = g.BY == 8 ? 3 : g.BY == 4 ? 2 : g.BY == 2 ? 1 : 0;
 	g.nbx = g.nx / g.BX;
 	g.nby = g.ny / g.BY;
 	g.nby_glob = g.nby * p.nranks;
@@ -268,7 +270,9 @@ cpic_b200_create(const cpic_b200_params_t *pp, cpic_b200_sim_t **out)
 	if(!rc) rc = make_tensor_map(&s->mapEy, s->Ey, g);
 	if(rc) { cpic_b200_destroy(s); return rc; }
 
-	s->smem_push = 128 + 2 * tile_bytes(g);
+	/* barrier + per-warp scratch + two E tiles + per-warp prefetch rings (sized for the
+	 * widest mode: 8 arrays) */
+	s->smem_push = 128 + MAX_WPC * 32 * sizeof(int) + 2 * tile_bytes(g);
 	s->smem_dep = (size_t) g.WPC * (g.BX + 1) * (g.BY + 1) * sizeof(double);
 
 	for(int i = 0; i < p.nspecies; i++) { s->sp[i].q = p.q[i]; s->sp[i].m = p.m[i]; }
@@ -344,6 +348,8 @@ alloc_species(sim_t_ *s, int is, int cap)
 	h.d.ocs = ocs;
 	h.d.occ = occ;
 	h.d.obox = 4 * ocs + 4 * occ;
+	if((double) s->nb * cap >= 4294967296.0 || (double) s->nob * h.d.obox >= 4294967296.0)
+		return fail(CPIC_B200_EINVAL, "species %d needs more than 2^32 particle slots on one GPU; lower capacity_factor / outbox_fraction or use more ranks", is);
 	const size_t oslot = (size_t) s->nob * h.d.obox;
 	const size_t oarr = align256(oslot * sizeof(double));
 	const size_t ocnt = align256((size_t) s->nob * 9 * sizeof(int));
@@ -679,15 +685,16 @@ launch_gather_push(sim_t_ *s, int is)
 	if(!h.block) return 0;
 	const Geom &g = s->g;
 	static bool attr_set[3] = { false, false, false };
-	if(!attr_set[MODE] || s->smem_push > 48 * 1024)
+	const size_t smem = s->smem_push + (size_t) g.WPC * PIPE_STAGES * PipeArrays<MODE>::N * 32 * sizeof(double);
+	if(!attr_set[MODE] || smem > 48 * 1024)
 	{
-		CK(cudaFuncSetAttribute(k_gather_push<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) s->smem_push));
+		CK(cudaFuncSetAttribute(k_gather_push<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 		attr_set[MODE] = true;
 	}
 	const int ctas = s->nb / g.WPC;
 	/* a push reads the pending arrivals and fills the other outbox */
 	const int cur = MODE == 0 ? h.arr : h.arr ^ 1;
-	k_gather_push<MODE><<<ctas, 32 * g.WPC, s->smem_push, s->stream>>>(h.d, g, push_params(s, is),
+	k_gather_push<MODE><<<ctas, 32 * g.WPC, smem, s->stream>>>(h.d, g, push_params(s, is),
 			s->mapEx, s->mapEy, s->nb, cur, s->errflag);
 	if(MODE != 0) h.arr = cur;
 	return check_launch(s);
