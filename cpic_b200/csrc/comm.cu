@@ -1,11 +1,355 @@
-/* placeholder, replaced below */
+/* Multi-GPU layer of cpic_b200: one Y slab per rank, NCCL point-to-point over NVLink.
+ *
+ * What travels (reference -> here):
+ *   rho ghost row      src/comm_field.c:51-136   ncclSend/Recv of nx doubles on the rank ring
+ *   phi ghost rows     src/comm_field.c:139-201  2 rows north, 1 row south, padding included
+ *   particles (Y pass) src/comm_plasma.c:887-1120  the outbox regions of the edge block rows
+ *                      that point across the slab face, straight into the neighbour's ghost
+ *                      outbox rows (no packing: regions are stored code-major)
+ *   FFT transposes     FFTW-MPI inside src/solver.c:485,491: row FFTs, all-to-all, column
+ *                      FFTs with the Green's function applied in the transposed layout,
+ *                      all-to-all back, row FFTs (2 exchanges per solve; FFTW does 4)
+ *
+ * NCCL is resolved at run time (dlopen "libnccl.so.2", the copy PyTorch already loaded
+ * when the ranks were started by torchrun), so the library also loads where NCCL is absent.
+ */
 #include "comm.h"
+#include "kernels.cuh"
+
+#include <cufft.h>
+#include <dlfcn.h>
+#include <math.h>
 #include <stdio.h>
-struct Comm { int dummy; };
-int comm_unique_id(void *, char *err, size_t n) { snprintf(err, n, "multi-rank support not built"); return 2; }
-Comm *comm_create(const void *, int, int, const Geom &, cudaStream_t, char *err, size_t n) { snprintf(err, n, "multi-rank support not built"); return NULL; }
-void comm_destroy(Comm *) {}
-int comm_rho_halo(Comm *, double *, cudaStream_t, long long *) { return 2; }
-int comm_phi_halo(Comm *, double *, cudaStream_t) { return 2; }
-int comm_particles(Comm *, SpeciesDev *, int, const Geom &, int, cudaStream_t, int *, long long *) { return 2; }
-int comm_solve(Comm *, const double *, double *, cudaStream_t, long long *) { return 2; }
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+/* ---- the part of nccl.h that is used (stable ABI since NCCL 2.7) ---- */
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+enum { ncclInt8 = 0, ncclInt32 = 2, ncclInt64 = 4, ncclFloat64 = 8 };
+
+struct Nccl {
+	void *lib;
+	ncclResult_t (*GetUniqueId)(ncclUniqueId *);
+	ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
+	ncclResult_t (*CommDestroy)(ncclComm_t);
+	ncclResult_t (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t);
+	ncclResult_t (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t);
+	ncclResult_t (*GroupStart)(void);
+	ncclResult_t (*GroupEnd)(void);
+	const char *(*GetErrorString)(ncclResult_t);
+};
+
+static Nccl g_nccl;
+
+static int
+load_nccl(char *err, size_t errlen)
+{
+	if(g_nccl.lib) return 0;
+	const char *names[] = { getenv("CPIC_B200_NCCL"), "libnccl.so.2", "libnccl.so" };
+	void *lib = NULL;
+	for(const char *n : names)
+	{
+		if(!n || !*n) continue;
+		lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+		if(lib) break;
+	}
+	if(!lib)
+	{
+		snprintf(err, errlen, "cannot load NCCL (libnccl.so.2): %s; set CPIC_B200_NCCL to its path", dlerror());
+		return 2;
+	}
+#define SYM(field, name) do { *(void **) &g_nccl.field = dlsym(lib, name); \
+	if(!g_nccl.field) { snprintf(err, errlen, "NCCL symbol %s missing", name); return 2; } } while(0)
+	SYM(GetUniqueId, "ncclGetUniqueId");
+	SYM(CommInitRank, "ncclCommInitRank");
+	SYM(CommDestroy, "ncclCommDestroy");
+	SYM(Send, "ncclSend");
+	SYM(Recv, "ncclRecv");
+	SYM(GroupStart, "ncclGroupStart");
+	SYM(GroupEnd, "ncclGroupEnd");
+	SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+	g_nccl.lib = lib;
+	return 0;
+}
+
+struct Comm {
+	ncclComm_t nc;
+	int rank, n;
+	Geom g;
+	char *err;
+	size_t errlen;
+
+	double *rho_recv;            /* nx doubles */
+
+	/* distributed FFT */
+	int nc_, cw;                 /* complex columns nx/2+1; columns per rank (ceil) */
+	cufftHandle rows_fwd, rows_inv, cols;
+	cufftDoubleComplex *a;       /* ny_loc x nc   row spectra */
+	cufftDoubleComplex *sb;      /* n blocks of ny_loc x cw   (send / receive staging) */
+	cufftDoubleComplex *tb;      /* ny_glob x cw  this rank's columns, all rows */
+	double *GT;                  /* ny_glob x cw  Green's function in that layout */
+};
+
+#define NCK(call) do { ncclResult_t r_ = (call); if(r_ != 0) { \
+	snprintf(c->err, c->errlen, "%s:%d: %s: %s", __FILE__, __LINE__, #call, g_nccl.GetErrorString(r_)); return 2; } } while(0)
+#define CCK(call) do { cudaError_t e_ = (call); if(e_ != cudaSuccess) { \
+	snprintf(c->err, c->errlen, "%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); return 2; } } while(0)
+#define FCK(call) do { cufftResult r_ = (call); if(r_ != CUFFT_SUCCESS) { \
+	snprintf(c->err, c->errlen, "%s:%d: %s: cufft error %d", __FILE__, __LINE__, #call, (int) r_); return 2; } } while(0)
+
+int
+comm_unique_id(void *id128, char *err, size_t errlen)
+{
+	int rc = load_nccl(err, errlen);
+	if(rc) return rc;
+	ncclUniqueId id;
+	ncclResult_t r = g_nccl.GetUniqueId(&id);
+	if(r != 0)
+	{
+		snprintf(err, errlen, "ncclGetUniqueId: %s", g_nccl.GetErrorString(r));
+		return 2;
+	}
+	memcpy(id128, &id, sizeof(id));
+	return 0;
+}
+
+static int
+comm_setup(Comm *c, const void *id128, cudaStream_t stream)
+{
+	const Geom &g = c->g;
+	ncclUniqueId id;
+	memcpy(&id, id128, sizeof(id));
+	NCK(g_nccl.CommInitRank(&c->nc, c->n, id, c->rank));
+
+	CCK(cudaMalloc(&c->rho_recv, (size_t) g.nx * sizeof(double)));
+
+	c->nc_ = g.nx / 2 + 1;
+	c->cw = (c->nc_ + c->n - 1) / c->n;
+	const size_t blk = (size_t) g.ny * c->cw;
+	CCK(cudaMalloc(&c->a, (size_t) g.ny * c->nc_ * sizeof(cufftDoubleComplex)));
+	CCK(cudaMalloc(&c->sb, blk * c->n * sizeof(cufftDoubleComplex)));
+	CCK(cudaMalloc(&c->tb, blk * c->n * sizeof(cufftDoubleComplex)));
+
+	/* MFT_init, reference src/solver.c:257-280: G[l][k] for this rank's columns, all rows */
+	std::vector<double> GT((size_t) g.ny_glob * c->cw, 0.0);
+	const double cx = 2.0 * M_PI / (double) g.nx, cy = 2.0 * M_PI / (double) g.ny_glob;
+	for(int iy = 0; iy < g.ny_glob; iy++)
+		for(int kl = 0; kl < c->cw; kl++)
+		{
+			const int ix = c->rank * c->cw + kl;
+			if(ix >= c->nc_) continue;
+			GT[(size_t) iy * c->cw + kl] = (ix == 0 && iy == 0) ? 0.0 :
+				1.0 / (2.0 * (cos(cx * (double) ix) + cos(cy * (double) iy)) - 4.0);
+		}
+	CCK(cudaMalloc(&c->GT, GT.size() * sizeof(double)));
+	CCK(cudaMemcpy(c->GT, GT.data(), GT.size() * sizeof(double), cudaMemcpyHostToDevice));
+
+	int nrow[1] = { g.nx };
+	int rembed[1] = { g.S }, cembed[1] = { c->nc_ };
+	FCK(cufftPlanMany(&c->rows_fwd, 1, nrow, rembed, 1, g.S, cembed, 1, c->nc_, CUFFT_D2Z, g.ny));
+	FCK(cufftPlanMany(&c->rows_inv, 1, nrow, cembed, 1, c->nc_, rembed, 1, g.S, CUFFT_Z2D, g.ny));
+	int ncol[1] = { g.ny_glob };
+	int embed[1] = { g.ny_glob };
+	/* column k of the ny_glob x cw array: stride cw between rows, 1 between columns */
+	FCK(cufftPlanMany(&c->cols, 1, ncol, embed, c->cw, 1, embed, c->cw, 1, CUFFT_Z2Z, c->cw));
+	FCK(cufftSetStream(c->rows_fwd, stream));
+	FCK(cufftSetStream(c->rows_inv, stream));
+	FCK(cufftSetStream(c->cols, stream));
+	return 0;
+}
+
+Comm *
+comm_create(const void *id128, int rank, int nranks, const Geom &g, cudaStream_t stream,
+		char *err, size_t errlen)
+{
+	if(load_nccl(err, errlen)) return NULL;
+	Comm *c = new Comm();
+	memset(c, 0, sizeof(*c));
+	c->rank = rank;
+	c->n = nranks;
+	c->g = g;
+	c->err = err;
+	c->errlen = errlen;
+	if(comm_setup(c, id128, stream))
+	{
+		comm_destroy(c);
+		return NULL;
+	}
+	return c;
+}
+
+void
+comm_destroy(Comm *c)
+{
+	if(!c) return;
+	if(c->rows_fwd) cufftDestroy(c->rows_fwd);
+	if(c->rows_inv) cufftDestroy(c->rows_inv);
+	if(c->cols) cufftDestroy(c->cols);
+	cudaFree(c->rho_recv); cudaFree(c->a); cudaFree(c->sb); cudaFree(c->tb); cudaFree(c->GT);
+	if(c->nc) g_nccl.CommDestroy(c->nc);
+	delete c;
+}
+
+/* comm_send_ghost_rho + comm_recv_ghost_rho, reference src/comm_field.c:51-136 */
+int
+comm_rho_halo(Comm *c, double *rho, cudaStream_t stream, long long *launches)
+{
+	const Geom &g = c->g;
+	const int south = (c->rank + 1) % c->n, north = (c->rank + c->n - 1) % c->n;
+	NCK(g_nccl.GroupStart());
+	NCK(g_nccl.Send(rho + (size_t) g.ny * g.S, (size_t) g.nx, ncclFloat64, south, c->nc, stream));
+	NCK(g_nccl.Recv(c->rho_recv, (size_t) g.nx, ncclFloat64, north, c->nc, stream));
+	NCK(g_nccl.GroupEnd());
+	k_rho_fold<<<(g.nx + 127) / 128, 128, 0, stream>>>(rho, c->rho_recv, g);
+	CCK(cudaGetLastError());
+	if(launches) (*launches)++;
+	return 0;
+}
+
+/* comm_phi_send + comm_phi_recv, reference src/comm_field.c:139-201 */
+int
+comm_phi_halo(Comm *c, double *phi, cudaStream_t stream)
+{
+	const Geom &g = c->g;
+	const int south = (c->rank + 1) % c->n, north = (c->rank + c->n - 1) % c->n;
+	const size_t S = (size_t) g.S;
+	NCK(g_nccl.GroupStart());
+	/* slab rows 0,1 (array rows 1,2) -> north rank's two south ghost rows */
+	NCK(g_nccl.Send(phi + 1 * S, 2 * S, ncclFloat64, north, c->nc, stream));
+	/* slab row ny-1 (array row ny) -> south rank's north ghost row */
+	NCK(g_nccl.Send(phi + (size_t) g.ny * S, S, ncclFloat64, south, c->nc, stream));
+	NCK(g_nccl.Recv(phi + (size_t) (g.ny + 1) * S, 2 * S, ncclFloat64, south, c->nc, stream));
+	NCK(g_nccl.Recv(phi, S, ncclFloat64, north, c->nc, stream));
+	NCK(g_nccl.GroupEnd());
+	return 0;
+}
+
+/* The Y pass of comm_plasma between ranks (reference src/comm_plasma.c:1039-1120).
+ * Row 0's regions with codes 0,1,2 (moving north) land in the north rank's south ghost
+ * row; the last row's regions with codes 6,7,8 in the south rank's north ghost row.
+ * Whole regions travel (their live prefix is given by the counts that go with them). */
+int
+comm_particles(Comm *c, SpeciesDev *sp, int arr, const Geom &g, int nb, cudaStream_t stream,
+		int *errflag, long long *launches)
+{
+	(void) errflag; (void) launches;
+	const Outbox &ob = sp->ob[arr];
+	const int south = (c->rank + 1) % c->n, north = (c->rank + c->n - 1) % c->n;
+	const int nbx = g.nbx;
+	const int last = nb - nbx;               /* first block of the last row */
+	const int gn = nb, gs = nb + nbx;        /* ghost rows: north, south */
+	double *arrs[5] = { ob.x, ob.y, ob.ux, ob.uy, ob.uz };
+
+	NCK(g_nccl.GroupStart());
+	for(int k = 0; k < 3; k++)
+	{
+		const int cn = k, cs = 6 + k;        /* code moving north / south */
+		const size_t nslot_n = (size_t) nbx * sp->rcap[cn], nslot_s = (size_t) nbx * sp->rcap[cs];
+		const size_t to_n = sp->roff[cn], to_s = sp->roff[cs] + (size_t) last * sp->rcap[cs];
+		/* received: codes 0,1,2 come from the south rank's row 0 into our south ghost row,
+		 * codes 6,7,8 from the north rank's last row into our north ghost row */
+		const size_t fr_s = sp->roff[cn] + (size_t) gs * sp->rcap[cn];
+		const size_t fr_n = sp->roff[cs] + (size_t) gn * sp->rcap[cs];
+		for(double *a : arrs)
+		{
+			NCK(g_nccl.Send(a + to_n, nslot_n, ncclFloat64, north, c->nc, stream));
+			NCK(g_nccl.Send(a + to_s, nslot_s, ncclFloat64, south, c->nc, stream));
+			NCK(g_nccl.Recv(a + fr_s, nslot_n, ncclFloat64, south, c->nc, stream));
+			NCK(g_nccl.Recv(a + fr_n, nslot_s, ncclFloat64, north, c->nc, stream));
+		}
+		NCK(g_nccl.Send(ob.id + to_n, nslot_n, ncclInt64, north, c->nc, stream));
+		NCK(g_nccl.Send(ob.id + to_s, nslot_s, ncclInt64, south, c->nc, stream));
+		NCK(g_nccl.Recv(ob.id + fr_s, nslot_n, ncclInt64, south, c->nc, stream));
+		NCK(g_nccl.Recv(ob.id + fr_n, nslot_s, ncclInt64, north, c->nc, stream));
+		if(ob.Ex)
+		{
+			double *es[2] = { ob.Ex, ob.Ey };
+			for(double *a : es)
+			{
+				NCK(g_nccl.Send(a + to_n, nslot_n, ncclFloat64, north, c->nc, stream));
+				NCK(g_nccl.Send(a + to_s, nslot_s, ncclFloat64, south, c->nc, stream));
+				NCK(g_nccl.Recv(a + fr_s, nslot_n, ncclFloat64, south, c->nc, stream));
+				NCK(g_nccl.Recv(a + fr_n, nslot_s, ncclFloat64, north, c->nc, stream));
+			}
+		}
+		/* counts: [code][block] */
+		NCK(g_nccl.Send(ob.count + (size_t) cn * sp->nob, (size_t) nbx, ncclInt32, north, c->nc, stream));
+		NCK(g_nccl.Send(ob.count + (size_t) cs * sp->nob + last, (size_t) nbx, ncclInt32, south, c->nc, stream));
+		NCK(g_nccl.Recv(ob.count + (size_t) cn * sp->nob + gs, (size_t) nbx, ncclInt32, south, c->nc, stream));
+		NCK(g_nccl.Recv(ob.count + (size_t) cs * sp->nob + gn, (size_t) nbx, ncclInt32, north, c->nc, stream));
+	}
+	NCK(g_nccl.GroupEnd());
+	return 0;
+}
+
+/* ---- distributed MFT solve ---- */
+
+/* a[iy][k] (ny x nc) -> sb[r][iy][kl] with k = r*cw + kl (zero beyond nc) */
+__global__ void
+k_fft_pack(const cufftDoubleComplex *__restrict__ a, cufftDoubleComplex *__restrict__ sb,
+		int ny, int nc, int cw, int n)
+{
+	const int k = blockIdx.x * blockDim.x + threadIdx.x;     /* padded column */
+	const int iy = blockIdx.y;
+	if(k >= cw * n) return;
+	const int r = k / cw, kl = k % cw;
+	cufftDoubleComplex v = { 0.0, 0.0 };
+	if(k < nc) v = a[(size_t) iy * nc + k];
+	sb[((size_t) r * ny + iy) * cw + kl] = v;
+}
+
+__global__ void
+k_fft_unpack(const cufftDoubleComplex *__restrict__ sb, cufftDoubleComplex *__restrict__ a,
+		int ny, int nc, int cw)
+{
+	const int k = blockIdx.x * blockDim.x + threadIdx.x;
+	const int iy = blockIdx.y;
+	if(k >= nc) return;
+	const int r = k / cw, kl = k % cw;
+	a[(size_t) iy * nc + k] = sb[((size_t) r * ny + iy) * cw + kl];
+}
+
+static int
+all_to_all(Comm *c, cufftDoubleComplex *send, cufftDoubleComplex *recv, cudaStream_t stream)
+{
+	const size_t blk = (size_t) c->g.ny * c->cw;             /* complex elements per pair */
+	NCK(g_nccl.GroupStart());
+	for(int r = 0; r < c->n; r++)
+	{
+		if(r == c->rank) continue;
+		NCK(g_nccl.Send(send + r * blk, 2 * blk, ncclFloat64, r, c->nc, stream));
+		NCK(g_nccl.Recv(recv + r * blk, 2 * blk, ncclFloat64, r, c->nc, stream));
+	}
+	NCK(g_nccl.GroupEnd());
+	CCK(cudaMemcpyAsync(recv + c->rank * blk, send + c->rank * blk, blk * sizeof(cufftDoubleComplex),
+				cudaMemcpyDeviceToDevice, stream));
+	return 0;
+}
+
+/* MFT_solve, reference src/solver.c:465-509, over the ranks: rho slab rows -> unnormalised
+ * phi slab rows (MFT_normalize is applied by k_phi_finish) */
+int
+comm_solve(Comm *c, const double *rho, double *phi_raw, cudaStream_t stream, long long *launches)
+{
+	const Geom &g = c->g;
+	const int ncp = c->cw * c->n;
+	FCK(cufftExecD2Z(c->rows_fwd, (double *) rho, c->a));
+	k_fft_pack<<<dim3((ncp + 127) / 128, g.ny), 128, 0, stream>>>(c->a, c->sb, g.ny, c->nc_, c->cw, c->n);
+	if(all_to_all(c, c->sb, c->tb, stream)) return 2;
+	FCK(cufftExecZ2Z(c->cols, c->tb, c->tb, CUFFT_FORWARD));
+	const size_t n = (size_t) g.ny_glob * c->cw;
+	int blocks = (int) ((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+	k_green<<<blocks, 256, 0, stream>>>(c->tb, c->GT, n);
+	FCK(cufftExecZ2Z(c->cols, c->tb, c->tb, CUFFT_INVERSE));
+	if(all_to_all(c, c->tb, c->sb, stream)) return 2;
+	k_fft_unpack<<<dim3((c->nc_ + 127) / 128, g.ny), 128, 0, stream>>>(c->sb, c->a, g.ny, c->nc_, c->cw);
+	FCK(cufftExecZ2D(c->rows_inv, c->a, phi_raw));
+	CCK(cudaGetLastError());
+	if(launches) *launches += 3;
+	return 0;
+}

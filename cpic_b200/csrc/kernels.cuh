@@ -24,16 +24,19 @@
 #define FULL 0xffffffffu
 #define MAX_WPC 8
 
-/* Outbox of every block: the particles that left it in one push, one region per
- * destination code (geom.h) so that the receiving block finds its arrivals as contiguous
- * runs: four side regions of `ocs` slots (codes 1,3,5,7) and four corner regions of
- * `occ` slots (codes 0,2,6,8), `obox` slots per block. Two of them alternate: a push
- * reads the arrivals of the previous push from one and fills the other. */
+/* Outbox: the particles that left their block in one push, one region per block and
+ * destination code (geom.h), so that the receiving block finds its arrivals as
+ * contiguous runs. Regions are stored code-major -- all blocks' code-0 regions, then all
+ * code-1 regions ... -- so that what one block row sends across a slab face (codes 0,1,2
+ * of row 0, codes 6,7,8 of the last row) is three contiguous chunks per array and can be
+ * handed to NCCL without packing. Side regions (codes 1,3,5,7) hold `ocs` slots, corner
+ * regions (0,2,6,8) `occ`. Two outboxes alternate: a push reads the arrivals of the
+ * previous push from one and fills the other. */
 struct Outbox {
 	double *x, *y, *ux, *uy, *uz;
 	double *Ex, *Ey;         /* travel with the particle when the per-particle E is kept */
 	long long *id;
-	int *count;              /* 9 per block: leavers per destination code ([4] unused) */
+	int *count;              /* [code][block]: leavers of that block with that destination */
 };
 
 /* Device view of one species */
@@ -43,22 +46,18 @@ struct SpeciesDev {
 	long long *id;
 	int *count;              /* particles in the block's own segment */
 	Outbox ob[2];
-	int cap, ocs, occ, obox;
+	int cap;                 /* slots per block segment */
+	int ocs, occ;            /* slots per side / corner region */
+	int nob;                 /* blocks that own an outbox: the slab's, plus two ghost rows with several ranks */
+	unsigned roff[9];        /* first slot of the regions of code c */
+	int rcap[9];             /* slots per region of code c (0 for code 4) */
 };
 
-/* First slot of the region of destination code c inside a block's outbox */
-__host__ __device__ __forceinline__ int
-region_base(const SpeciesDev &sp, int c)
+/* Slot of entry `pos` in the region (block b, destination code c) */
+__device__ __forceinline__ unsigned
+region_slot(const SpeciesDev &sp, int c, int b, int pos)
 {
-	const int sides = (c > 1) + (c > 3) + (c > 5) + (c > 7);
-	const int corners = (c > 0) + (c > 2) + (c > 6);
-	return sides * sp.ocs + corners * sp.occ;
-}
-
-__host__ __device__ __forceinline__ int
-region_cap(const SpeciesDev &sp, int c)
-{
-	return (c & 1) ? sp.ocs : sp.occ;
+	return sp.roff[c] + (unsigned) b * (unsigned) sp.rcap[c] + (unsigned) pos;
 }
 
 /* Everything the mover needs besides the particle (reference src/mover.c:191-226) */
@@ -145,7 +144,7 @@ cp_async_wait()
 
 /* MFT_kernel, reference src/solver.c:337-363: g[l][k] *= G[l][k]. 16 B per element
  * read + 8 B of G + 16 B written: HBM-bound streaming. */
-__global__ void
+static __global__ void
 k_green(cufftDoubleComplex *__restrict__ g, const double *__restrict__ G, size_t n)
 {
 	size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
@@ -165,7 +164,7 @@ k_green(cufftDoubleComplex *__restrict__ g, const double *__restrict__ G, size_t
  * the south ghosts, row ny-1 the north ghost). `raw` is the Z2D output (ny x S), `phi`
  * the ny+3 row array. With several ranks only the slab rows are written here and the
  * ghosts arrive over NCCL. */
-__global__ void
+static __global__ void
 k_phi_finish(const double *__restrict__ raw, double *__restrict__ phi, Geom g, double N,
 		int fill_ghosts)
 {
@@ -186,7 +185,7 @@ k_phi_finish(const double *__restrict__ raw, double *__restrict__ phi, Geom g, d
  * [0, ny], X periodic, Y through the ghost rows. Also fills the wrap columns
  * [nx, SE) of the device E arrays (column nx+j repeats column j) so that a particle
  * block at the right edge can fetch its tile with one TMA box. */
-__global__ void
+static __global__ void
 k_field_E(const double *__restrict__ phi, double *__restrict__ Ex, double *__restrict__ Ey,
 		Geom g)
 {
@@ -206,7 +205,7 @@ k_field_E(const double *__restrict__ phi, double *__restrict__ Ex, double *__res
  * k_deposit left in hb (bottom rows), hr (right columns) and hc (corners) to the nodes
  * they belong to. Row ny (the south ghost row of `_rho`) is owned by nobody and is
  * assembled here from scratch. Grid: (ceil(nx/128), nby) -- rows y = (by+1)*BY. */
-__global__ void
+static __global__ void
 k_stitch_rows(double *__restrict__ rho, const double *__restrict__ hb,
 		const double *__restrict__ hr, const double *__restrict__ hc, Geom g)
 {
@@ -227,7 +226,7 @@ k_stitch_rows(double *__restrict__ rho, const double *__restrict__ hb,
 }
 
 /* Right-column halos for the rows k_stitch_rows does not visit. Grid: (ceil(ny/128), ncx) */
-__global__ void
+static __global__ void
 k_stitch_cols(double *__restrict__ rho, const double *__restrict__ hr, Geom g)
 {
 	int y = blockIdx.x * blockDim.x + threadIdx.x;
@@ -242,7 +241,7 @@ k_stitch_cols(double *__restrict__ rho, const double *__restrict__ hr, Geom g)
 /* Single rank: the ghost row goes to ourselves and is added to row 0
  * (reference src/comm_field.c:51-136). With several ranks `recv` is the row received
  * from rank-1. */
-__global__ void
+static __global__ void
 k_rho_fold(double *__restrict__ rho, const double *__restrict__ recv, Geom g)
 {
 	int x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -315,7 +314,7 @@ struct Arrivals {
 };
 
 __device__ __forceinline__ Arrivals
-find_arrivals(const Outbox &in, const Geom &g, int nb, int b, int lane, int *scratch)
+find_arrivals(const Outbox &in, int sp_nob, const Geom &g, int nb, int b, int lane, int *scratch)
 {
 	const int bx = b % g.nbx, by = b / g.nbx;
 	int src = 0, a_k = 0;
@@ -332,7 +331,7 @@ find_arrivals(const Outbox &in, const Geom &g, int nb, int b, int lane, int *scr
 		else if(nby_ < 0) src = nb + nbx_;                 /* north ghost row */
 		else if(nby_ >= g.nby) src = nb + g.nbx + nbx_;    /* south ghost row */
 		else src = nby_ * g.nbx + nbx_;
-		a_k = in.count[(size_t) src * 9 + (8 - lane)];
+		a_k = in.count[(size_t) (8 - lane) * sp_nob + src];
 	}
 	int apre = a_k;
 	for(int o = 1; o < 16; o <<= 1)
@@ -350,13 +349,13 @@ find_arrivals(const Outbox &in, const Geom &g, int nb, int b, int lane, int *scr
 }
 
 /* Outbox slot of arrival f (0 <= f < A.total) */
-__device__ __forceinline__ size_t
+__device__ __forceinline__ unsigned
 arrival_slot(const Arrivals &A, const SpeciesDev &sp, int f)
 {
 	int k = 0;
 #pragma unroll
 	for(int q = 1; q < 9; q++) if(f >= A.start[q]) k = q;
-	return (size_t) A.src[k] * sp.obox + region_base(sp, 8 - k) + (f - A.start[k]);
+	return region_slot(sp, 8 - k, A.src[k], f - A.start[k]);
 }
 
 /* MODE 0: stage_plasma_E alone   (gather, store E per particle)
@@ -414,10 +413,9 @@ k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 	 * previous push's outbox and fills `cur` */
 	const Outbox &in = sp.ob[MODE == 0 ? cur : cur ^ 1];
 	const Outbox &out = sp.ob[cur];
-	const Arrivals A = find_arrivals(in, g, nb, b, lane, wscratch);
+	const Arrivals A = find_arrivals(in, sp.nob, g, nb, b, lane, wscratch);
 	const int cnt = sp.count[b];
 	const unsigned base = (unsigned) b * (unsigned) sp.cap;      /* slot indices fit 32 bits (checked on the host) */
-	const unsigned obase = (unsigned) b * (unsigned) sp.obox;
 	const int tx0 = cx * g.WPC * g.BX, ty0 = by * g.BY;   /* tile origin in cells */
 	const int gby = g.brow0 + by;
 	/* the walk: nbo batches over the own segment, then nba over the arrivals */
@@ -578,9 +576,9 @@ k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 				__syncwarp(ml);
 				if((peers & lt) == 0) ocnt[dest] = pos + __popc(peers);
 				if(dest == DEST_FAR) bad |= 4;
-				else if(pos < region_cap(sp, dest))
+				else if(pos < sp.rcap[dest])
 				{
-					const unsigned o = obase + region_base(sp, dest) + pos;
+					const unsigned o = region_slot(sp, dest, b, pos);
 					out.x[o] = x; out.y[o] = y;
 					out.ux[o] = ux; out.uy[o] = uy; out.uz[o] = uz;
 					out.id[o] = pid;
@@ -600,8 +598,8 @@ k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 		if(lane < 9)
 		{
 			const int v = ocnt[lane];
-			const int rc = region_cap(sp, lane);
-			out.count[(size_t) b * 9 + lane] = v < rc ? v : rc;
+			const int rc = sp.rcap[lane];
+			out.count[(size_t) lane * sp.nob + b] = v < rc ? v : rc;
 		}
 		if(bad)
 		{
@@ -617,7 +615,7 @@ k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 /* Appends the pending arrivals of every block (outbox `arr`) to its own segment and
  * clears the runs it consumed. Not on the per-step path: used before particles are
  * handed to the host (downloads, diagnostics). One warp per block. */
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 k_absorb(SpeciesDev sp, Geom g, int nb, int arr, int *__restrict__ errflag)
 {
 	const int lane = threadIdx.x & 31;
@@ -625,7 +623,7 @@ k_absorb(SpeciesDev sp, Geom g, int nb, int arr, int *__restrict__ errflag)
 	if(b >= nb) return;
 	__shared__ int scratch[8][18];
 	const Outbox &in = sp.ob[arr];
-	const Arrivals A = find_arrivals(in, g, nb, b, lane, scratch[threadIdx.x >> 5]);
+	const Arrivals A = find_arrivals(in, sp.nob, g, nb, b, lane, scratch[threadIdx.x >> 5]);
 	if(A.total == 0) return;
 	const int cnt = sp.count[b];
 	const size_t base = (size_t) b * sp.cap;
@@ -646,7 +644,7 @@ k_absorb(SpeciesDev sp, Geom g, int nb, int arr, int *__restrict__ errflag)
 	/* the runs are consumed: lane k clears the counter it read */
 	if(lane < 9 && lane != DEST_STAY)
 	{
-		in.count[(size_t) A.src[lane] * 9 + (8 - lane)] = 0;
+		in.count[(size_t) (8 - lane) * sp.nob + A.src[lane]] = 0;
 	}
 }
 
@@ -680,7 +678,7 @@ k_deposit(SpeciesDev sp, Geom g, double vq, int nb, int arr,
 
 	__shared__ int scratch[MAX_WPC][18];
 	const Outbox &in = sp.ob[arr];
-	const Arrivals A = find_arrivals(in, g, nb, b, lane, scratch[warp]);
+	const Arrivals A = find_arrivals(in, sp.nob, g, nb, b, lane, scratch[warp]);
 	const int cnt = sp.count[b];
 	const int T = cnt + A.total;
 	const size_t base = (size_t) b * sp.cap;
@@ -763,7 +761,7 @@ k_deposit(SpeciesDev sp, Geom g, double vq, int nb, int arr,
 
 /* Kinetic energy per species: sum(ux^2 + uy^2), reference src/sim.c:366-395 (compiled
  * out there). One warp per block, fixed order; block sums land in out[b]. */
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 k_kinetic(SpeciesDev sp, int nb, double *__restrict__ out)
 {
 	const int lane = threadIdx.x & 31;
@@ -782,7 +780,7 @@ k_kinetic(SpeciesDev sp, int nb, double *__restrict__ out)
 }
 
 /* Potential energy: per-row sum of rho*phi over the slab (reference src/sim.c:356-363) */
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 k_potential(const double *__restrict__ rho, const double *__restrict__ phi, Geom g,
 		double *__restrict__ out)
 {
@@ -803,7 +801,7 @@ k_potential(const double *__restrict__ rho, const double *__restrict__ phi, Geom
 }
 
 /* Fixed-order sum of n doubles by one CTA (n is a few thousand: block/row partials) */
-__global__ void __launch_bounds__(1024)
+static __global__ void __launch_bounds__(1024)
 k_sum(const double *__restrict__ in, int n, double *__restrict__ out)
 {
 	__shared__ double part[1024];
@@ -833,7 +831,7 @@ u01(uint64_t &s)
 	return (double) (z >> 11) * (1.0 / 9007199254740992.0);
 }
 
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 k_init_uniform(SpeciesDev sp, Geom g, int nb, long long n, long long id0, double vx, double vy,
 		uint64_t seed)
 {

@@ -340,17 +340,25 @@ alloc_species(sim_t_ *s, int is, int cap)
 	h.d.count = (int *) (b + 6 * arr);
 	h.d.cap = cap;
 
-	/* outbox regions: four sides of ocs slots, four corners of occ */
+	/* outbox regions: four sides of ocs slots, four corners of occ, stored code-major */
 	double frac = s->p.outbox_fraction > 0 ? s->p.outbox_fraction : 0.3;
 	int ocs = (((int) ceil(cap * frac) + 31) / 32) * 32;
 	if(ocs < 32) ocs = 32;
 	int occ = ((ocs / 4 + 31) / 32) * 32;
 	h.d.ocs = ocs;
 	h.d.occ = occ;
-	h.d.obox = 4 * ocs + 4 * occ;
-	if((double) s->nb * cap >= 4294967296.0 || (double) s->nob * h.d.obox >= 4294967296.0)
+	h.d.nob = s->nob;
+	const double oslots = (double) s->nob * (4.0 * ocs + 4.0 * occ);
+	if((double) s->nb * cap >= 4294967296.0 || oslots >= 4294967296.0)
 		return fail(CPIC_B200_EINVAL, "species %d needs more than 2^32 particle slots on one GPU; lower capacity_factor / outbox_fraction or use more ranks", is);
-	const size_t oslot = (size_t) s->nob * h.d.obox;
+	unsigned off = 0;
+	for(int c = 0; c < 9; c++)
+	{
+		h.d.rcap[c] = c == DEST_STAY ? 0 : ((c & 1) ? ocs : occ);
+		h.d.roff[c] = off;
+		off += (unsigned) s->nob * (unsigned) h.d.rcap[c];
+	}
+	const size_t oslot = off;
 	const size_t oarr = align256(oslot * sizeof(double));
 	const size_t ocnt = align256((size_t) s->nob * 9 * sizeof(int));
 	const size_t one = 6 * oarr + ocnt;
@@ -381,7 +389,7 @@ ensure_particle_E(sim_t_ *s, int is)
 	SpeciesHost &h = s->sp[is];
 	if(h.d.pEx || !h.block) return 0;
 	const size_t arr = align256((size_t) s->nb * h.d.cap * sizeof(double));
-	const size_t oarr = align256((size_t) s->nob * h.d.obox * sizeof(double));
+	const size_t oarr = align256(((size_t) h.d.roff[8] + (size_t) s->nob * h.d.rcap[8]) * sizeof(double));
 	CK(cudaMalloc(&h.pE, 2 * arr + 4 * oarr));
 	CK(cudaMemsetAsync(h.pE, 0, 2 * arr + 4 * oarr, s->stream));
 	h.d.pEx = h.pE;

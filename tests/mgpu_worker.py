@@ -1,0 +1,83 @@
+"""One rank of the multi-GPU parity test (launched by torchrun from test_gpu_multi.py):
+runs `steps` sim_steps of a conf on WORLD_SIZE GPUs and checks this rank's slab against the
+single-rank oracle, which every rank computes for itself."""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, HERE)
+
+import torch
+import torch.distributed as dist
+
+from cpic_b200 import Sim, load_conf, init_particles
+from cpic_b200.dist import env_rank, partition, bootstrap
+from _parity import oracle_from, relerr, TOL
+
+
+def main():
+    conf, steps = sys.argv[1], int(sys.argv[2])
+    fused = len(sys.argv) < 4 or sys.argv[3] == "fused"
+    rank, world, local = env_rank()
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    params, run = load_conf(conf, rank=rank, nranks=world, device=local)
+    parts = init_particles(conf)
+    o = oracle_from(params, parts)
+    g = Sim(params)
+    for i, p in enumerate(partition(parts, params, rank)):
+        g.set_particles(i, p["id"], p["x"], p["y"], p["ux"], p["uy"])
+    bootstrap(g, dist, device="cuda")
+    o.pre_step()
+    g.pre_step()
+    nyl = params.ny // world
+    r0 = rank * nyl
+    worst = {}
+
+    def check(tag):
+        g.sync()
+        e = {}
+        e["rho"] = relerr(g.field("rho"), o.field("rho")[r0:r0 + nyl])
+        og = o.field("phi_ghost")          # rows: -1, 0 .. ny-1, ny, ny+1 (periodic images)
+        rows = [(r0 - 1 + k) % params.ny for k in range(nyl + 3)]
+        e["phi"] = relerr(g.field("phi_ghost"), og[1:params.ny + 1][rows])
+        e["Ex"] = relerr(g.field("Ex"), o.field("Ex")[r0:r0 + nyl + 1])
+        e["Ey"] = relerr(g.field("Ey"), o.field("Ey")[r0:r0 + nyl + 1])
+        from cpic_b200.dist import slab_rank
+        for i in range(len(params.q)):
+            a, b = g.particles(i), o.particles(i)
+            sel = slab_rank(params, b["y"]) == rank
+            ids = b["id"][sel]
+            assert len(a["id"]) == len(ids) and (a["id"] == ids).all(), \
+                f"{tag}: rank {rank} species {i} holds {len(a['id'])} particles, the oracle puts {len(ids)} in its slab"
+            umax = max(np.abs(b["ux"]).max(initial=0), np.abs(b["uy"]).max(initial=0), 1e-300)
+            e[f"x{i}"] = np.abs(a["x"] - b["x"][sel]).max(initial=0) / params.Lx
+            e[f"y{i}"] = np.abs(a["y"] - b["y"][sel]).max(initial=0) / params.Ly
+            e[f"ux{i}"] = np.abs(a["ux"] - b["ux"][sel]).max(initial=0) / umax
+            e[f"uy{i}"] = np.abs(a["uy"] - b["uy"][sel]).max(initial=0) / umax
+        bad = {k: v for k, v in e.items() if not v <= TOL}
+        assert not bad, f"{tag}: rank {rank}: beyond {TOL}: {bad}"
+        for k, v in e.items():
+            worst[k] = max(worst.get(k, 0), v)
+
+    check("after sim_init")
+    for it in range(steps):
+        if fused:
+            g.step()
+        else:
+            g.step_staged()
+        o.step()
+        check(f"iteration {it}")
+    t = torch.tensor([max(worst.values())], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print(f"MGPU-OK world={world} conf={os.path.basename(conf)} steps={steps} worst={t.item():.2e}")
+    g.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

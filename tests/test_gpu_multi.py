@@ -1,0 +1,40 @@
+"""Multi-GPU parity (needs >= 2 GPUs): P Y-slabs over NCCL against the single-rank oracle."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import conf_path, ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def ngpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+def run_ranks(n, conf, steps, mode="fused", port=29611):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+           "--master-addr", "127.0.0.1", "--master-port", str(port),
+           os.path.join(ROOT, "tests", "mgpu_worker.py"), conf_path(conf), str(steps), mode]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "MGPU-OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("conf,mode", [("uniform-small.conf", "fused"), ("2d-2species-small.conf", "staged"),
+                                       ("two-streams.conf", "fused")])
+def test_two_ranks(conf, mode):
+    if ngpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    run_ranks(2, conf, 10, mode)
+
+
+def test_four_ranks():
+    if ngpus() < 4:
+        pytest.skip("needs 4 GPUs")
+    run_ranks(4, "uniform-small.conf", 10, "fused", port=29613)
