@@ -85,6 +85,8 @@ struct Comm {
 	size_t errlen;
 
 	double *rho_recv;            /* nx doubles */
+	double *face[4];             /* particle face buffers: send north/south, receive from south/north */
+	size_t face_cap;             /* doubles each */
 
 	/* distributed FFT */
 	int nc_, cw;                 /* complex columns nx/2+1; columns per rank (ceil) */
@@ -190,6 +192,7 @@ comm_destroy(Comm *c)
 	if(c->rows_fwd) cufftDestroy(c->rows_fwd);
 	if(c->rows_inv) cufftDestroy(c->rows_inv);
 	if(c->cols) cufftDestroy(c->cols);
+	for(int k = 0; k < 4; k++) cudaFree(c->face[k]);
 	cudaFree(c->rho_recv); cudaFree(c->a); cudaFree(c->sb); cudaFree(c->tb); cudaFree(c->GT);
 	if(c->nc) g_nccl.CommDestroy(c->nc);
 	delete c;
@@ -229,61 +232,115 @@ comm_phi_halo(Comm *c, double *phi, cudaStream_t stream)
 	return 0;
 }
 
+/* Pack / unpack of the regions that cross a slab face. A face buffer holds, for the three
+ * codes k of that direction and the NA arrays (x y ux uy uz id [Ex Ey]), the regions of
+ * the nbx edge blocks (nbx * rcap[code] values each), followed by the 3 * nbx counts. */
+struct FaceLayout {
+	unsigned off[3];         /* first value of code k's chunk (per array: nbx * rcap values) */
+	unsigned total;          /* doubles before the counts */
+	int na;
+};
+
+static __device__ __forceinline__ double *
+outbox_array(const Outbox &ob, int a)
+{
+	switch(a)
+	{
+		case 0: return ob.x;
+		case 1: return ob.y;
+		case 2: return ob.ux;
+		case 3: return ob.uy;
+		case 4: return ob.uz;
+		case 5: return (double *) ob.id;
+		case 6: return ob.Ex;
+		default: return ob.Ey;
+	}
+}
+
+/* dir 0: row 0, codes 0,1,2 (to the north rank); dir 1: last row, codes 6,7,8 (south).
+ * pack != 0: regions -> buffer; else buffer -> ghost rows (north buffer received from the
+ * south rank fills the south ghost row and vice versa). */
+static __global__ void __launch_bounds__(256)
+k_face_copy(SpeciesDev sp, int arr, int nbx, int first_block, int code0, FaceLayout L,
+		double *__restrict__ buf, int pack)
+{
+	const Outbox &ob = sp.ob[arr];
+	const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i < L.total)
+	{
+		int k = i >= L.off[2] ? 2 : i >= L.off[1] ? 1 : 0;
+		const int c = code0 + k;
+		const unsigned per = (unsigned) nbx * (unsigned) sp.rcap[c];      /* values per array */
+		const unsigned r = i - L.off[k];
+		const int a = r / per;
+		const unsigned j = r % per;                                       /* block-major inside the row */
+		double *p = outbox_array(ob, a) + sp.roff[c] + (unsigned) first_block * (unsigned) sp.rcap[c] + j;
+		if(pack) buf[i] = *p;
+		else *p = buf[i];
+	}
+	else if(i < L.total + 3u * nbx)
+	{
+		const unsigned r = i - L.total;
+		const int k = r / nbx, bx = r % nbx;
+		int *cnt = ob.count + (size_t) (code0 + k) * sp.nob + first_block + bx;
+		int *bc = (int *) (buf + L.total) + r;
+		if(pack) *bc = *cnt;
+		else *cnt = *bc;
+	}
+}
+
+static FaceLayout
+face_layout(const SpeciesDev *sp, int nbx, int code0)
+{
+	FaceLayout L;
+	L.na = sp->ob[0].Ex ? 8 : 6;
+	unsigned off = 0;
+	for(int k = 0; k < 3; k++)
+	{
+		L.off[k] = off;
+		off += (unsigned) L.na * (unsigned) nbx * (unsigned) sp->rcap[code0 + k];
+	}
+	L.total = off;
+	return L;
+}
+
 /* The Y pass of comm_plasma between ranks (reference src/comm_plasma.c:1039-1120).
  * Row 0's regions with codes 0,1,2 (moving north) land in the north rank's south ghost
  * row; the last row's regions with codes 6,7,8 in the south rank's north ghost row.
- * Whole regions travel (their live prefix is given by the counts that go with them). */
+ * One message per face: a small kernel gathers the regions and their counts into a
+ * contiguous buffer, NCCL moves it, another kernel scatters it into the ghost rows. */
 int
 comm_particles(Comm *c, SpeciesDev *sp, int arr, const Geom &g, int nb, cudaStream_t stream,
 		int *errflag, long long *launches)
 {
-	(void) errflag; (void) launches;
-	const Outbox &ob = sp->ob[arr];
+	(void) errflag;
 	const int south = (c->rank + 1) % c->n, north = (c->rank + c->n - 1) % c->n;
 	const int nbx = g.nbx;
-	const int last = nb - nbx;               /* first block of the last row */
-	const int gn = nb, gs = nb + nbx;        /* ghost rows: north, south */
-	double *arrs[5] = { ob.x, ob.y, ob.ux, ob.uy, ob.uz };
-
-	NCK(g_nccl.GroupStart());
-	for(int k = 0; k < 3; k++)
+	const FaceLayout Ln = face_layout(sp, nbx, 0), Ls = face_layout(sp, nbx, 6);
+	/* both layouts have the same size (corner, side, corner) */
+	const size_t doubles = (size_t) Ln.total + (3 * (size_t) nbx + 1) / 2;
+	if(doubles > c->face_cap)
 	{
-		const int cn = k, cs = 6 + k;        /* code moving north / south */
-		const size_t nslot_n = (size_t) nbx * sp->rcap[cn], nslot_s = (size_t) nbx * sp->rcap[cs];
-		const size_t to_n = sp->roff[cn], to_s = sp->roff[cs] + (size_t) last * sp->rcap[cs];
-		/* received: codes 0,1,2 come from the south rank's row 0 into our south ghost row,
-		 * codes 6,7,8 from the north rank's last row into our north ghost row */
-		const size_t fr_s = sp->roff[cn] + (size_t) gs * sp->rcap[cn];
-		const size_t fr_n = sp->roff[cs] + (size_t) gn * sp->rcap[cs];
-		for(double *a : arrs)
-		{
-			NCK(g_nccl.Send(a + to_n, nslot_n, ncclFloat64, north, c->nc, stream));
-			NCK(g_nccl.Send(a + to_s, nslot_s, ncclFloat64, south, c->nc, stream));
-			NCK(g_nccl.Recv(a + fr_s, nslot_n, ncclFloat64, south, c->nc, stream));
-			NCK(g_nccl.Recv(a + fr_n, nslot_s, ncclFloat64, north, c->nc, stream));
-		}
-		NCK(g_nccl.Send(ob.id + to_n, nslot_n, ncclInt64, north, c->nc, stream));
-		NCK(g_nccl.Send(ob.id + to_s, nslot_s, ncclInt64, south, c->nc, stream));
-		NCK(g_nccl.Recv(ob.id + fr_s, nslot_n, ncclInt64, south, c->nc, stream));
-		NCK(g_nccl.Recv(ob.id + fr_n, nslot_s, ncclInt64, north, c->nc, stream));
-		if(ob.Ex)
-		{
-			double *es[2] = { ob.Ex, ob.Ey };
-			for(double *a : es)
-			{
-				NCK(g_nccl.Send(a + to_n, nslot_n, ncclFloat64, north, c->nc, stream));
-				NCK(g_nccl.Send(a + to_s, nslot_s, ncclFloat64, south, c->nc, stream));
-				NCK(g_nccl.Recv(a + fr_s, nslot_n, ncclFloat64, south, c->nc, stream));
-				NCK(g_nccl.Recv(a + fr_n, nslot_s, ncclFloat64, north, c->nc, stream));
-			}
-		}
-		/* counts: [code][block] */
-		NCK(g_nccl.Send(ob.count + (size_t) cn * sp->nob, (size_t) nbx, ncclInt32, north, c->nc, stream));
-		NCK(g_nccl.Send(ob.count + (size_t) cs * sp->nob + last, (size_t) nbx, ncclInt32, south, c->nc, stream));
-		NCK(g_nccl.Recv(ob.count + (size_t) cn * sp->nob + gs, (size_t) nbx, ncclInt32, south, c->nc, stream));
-		NCK(g_nccl.Recv(ob.count + (size_t) cs * sp->nob + gn, (size_t) nbx, ncclInt32, north, c->nc, stream));
+		for(int k = 0; k < 4; k++) cudaFree(c->face[k]);
+		c->face_cap = doubles + doubles / 4;
+		for(int k = 0; k < 4; k++) CCK(cudaMalloc(&c->face[k], c->face_cap * sizeof(double)));
 	}
+	double *send_n = c->face[0], *send_s = c->face[1], *recv_s = c->face[2], *recv_n = c->face[3];
+	const unsigned threads = Ln.total + 3u * nbx;
+	const int blocks = (int) ((threads + 255) / 256);
+	k_face_copy<<<blocks, 256, 0, stream>>>(*sp, arr, nbx, 0, 0, Ln, send_n, 1);
+	k_face_copy<<<blocks, 256, 0, stream>>>(*sp, arr, nbx, nb - nbx, 6, Ls, send_s, 1);
+	NCK(g_nccl.GroupStart());
+	NCK(g_nccl.Send(send_n, doubles, ncclFloat64, north, c->nc, stream));
+	NCK(g_nccl.Send(send_s, doubles, ncclFloat64, south, c->nc, stream));
+	NCK(g_nccl.Recv(recv_s, doubles, ncclFloat64, south, c->nc, stream));
+	NCK(g_nccl.Recv(recv_n, doubles, ncclFloat64, north, c->nc, stream));
 	NCK(g_nccl.GroupEnd());
+	/* what the south rank sent north (codes 0,1,2) fills our south ghost row, and vice versa */
+	k_face_copy<<<blocks, 256, 0, stream>>>(*sp, arr, nbx, nb + nbx, 0, Ln, recv_s, 0);
+	k_face_copy<<<blocks, 256, 0, stream>>>(*sp, arr, nbx, nb, 6, Ls, recv_n, 0);
+	CCK(cudaGetLastError());
+	if(launches) *launches += 4;
 	return 0;
 }
 

@@ -51,7 +51,14 @@ struct SpeciesDev {
 	int nob;                 /* blocks that own an outbox: the slab's, plus two ghost rows with several ranks */
 	unsigned roff[9];        /* first slot of the regions of code c */
 	int rcap[9];             /* slots per region of code c (0 for code 4) */
+	/* particles that jumped further than a neighbouring block in one step (rare): a small
+	 * list, inserted by k_far_insert in id order */
+	double *fx, *fy, *fux, *fuy, *fuz, *fEx, *fEy;
+	long long *fid;
+	int *fcount;
 };
+
+#define FAR_CAP 2048
 
 /* Slot of entry `pos` in the region (block b, destination code c) */
 __device__ __forceinline__ unsigned
@@ -575,7 +582,18 @@ k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 				const int pos = ocnt[dest] + __popc(peers & lt);
 				__syncwarp(ml);
 				if((peers & lt) == 0) ocnt[dest] = pos + __popc(peers);
-				if(dest == DEST_FAR) bad |= 4;
+				if(dest == DEST_FAR)
+				{
+					const int k = atomicAdd(sp.fcount, 1);
+					if(k < FAR_CAP)
+					{
+						sp.fx[k] = x; sp.fy[k] = y;
+						sp.fux[k] = ux; sp.fuy[k] = uy; sp.fuz[k] = uz;
+						sp.fid[k] = pid;
+						sp.fEx[k] = Ex; sp.fEy[k] = Ey;
+					}
+					else bad |= 2;
+				}
 				else if(pos < sp.rcap[dest])
 				{
 					const unsigned o = region_slot(sp, dest, b, pos);
@@ -609,6 +627,67 @@ k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 			if(bad & 4) bits |= ERRBIT_FAR;
 			atomicOr(errflag, bits);
 		}
+	}
+}
+
+/* Far movers: the list filled by the push (in arbitrary order) is sorted by particle id
+ * by one CTA (bitonic sort in shared memory) and appended to the destination blocks'
+ * segments one by one, so the result does not depend on the order of arrival. A
+ * destination outside this rank's slab is an error (the reference bounds a step to one
+ * chunk, src/sim.c:198-200; here the bound across a slab face is one block row). */
+static __global__ void __launch_bounds__(1024)
+k_far_insert(SpeciesDev sp, Geom g, int *__restrict__ errflag)
+{
+	__shared__ long long key[FAR_CAP];
+	__shared__ int idx[FAR_CAP];
+	int n = *sp.fcount;
+	if(n == 0) return;
+	if(n > FAR_CAP) n = FAR_CAP;
+	int m = 1;
+	while(m < n) m <<= 1;
+	for(int i = threadIdx.x; i < m; i += blockDim.x)
+	{
+		key[i] = i < n ? sp.fid[i] : 0x7fffffffffffffffLL;
+		idx[i] = i;
+	}
+	__syncthreads();
+	for(int k = 2; k <= m; k <<= 1)
+		for(int j = k >> 1; j > 0; j >>= 1)
+		{
+			for(int i = threadIdx.x; i < m; i += blockDim.x)
+			{
+				const int l = i ^ j;
+				if(l > i)
+				{
+					const bool up = (i & k) == 0;
+					if((key[i] > key[l]) == up)
+					{
+						const long long tk = key[i]; key[i] = key[l]; key[l] = tk;
+						const int ti = idx[i]; idx[i] = idx[l]; idx[l] = ti;
+					}
+				}
+			}
+			__syncthreads();
+		}
+	if(threadIdx.x == 0)
+	{
+		for(int j = 0; j < n; j++)
+		{
+			const int e = idx[j];
+			const double x = sp.fx[e], y = sp.fy[e];
+			const int row = global_row(g, y);
+			if(row < g.row0 || row >= g.row0 + g.ny) { atomicOr(errflag, ERRBIT_FAR); continue; }
+			const int b = block_of(g, x, y);
+			const int pos = sp.count[b];
+			if(pos >= sp.cap) { atomicOr(errflag, ERRBIT_CAPACITY); continue; }
+			const size_t d = (size_t) b * sp.cap + pos;
+			sp.x[d] = x; sp.y[d] = y;
+			sp.ux[d] = sp.fux[e]; sp.uy[d] = sp.fuy[e]; sp.uz[d] = sp.fuz[e];
+			sp.id[d] = sp.fid[e];
+			if(sp.pEx) { sp.pEx[d] = sp.fEx[e]; sp.pEy[d] = sp.fEy[e]; }
+			sp.count[b] = pos + 1;
+		}
+		*sp.fcount = 0;
 	}
 }
 

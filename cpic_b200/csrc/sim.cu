@@ -50,6 +50,7 @@ struct SpeciesHost {
 	void *block;             /* one allocation: x y ux uy uz id count (the "image") */
 	size_t block_bytes;
 	void *oblock;            /* the two outboxes */
+	void *fblock;            /* far-mover list */
 	double *pE;              /* optional per-particle E (segment and outboxes) */
 	int arr;                 /* outbox that holds the pending arrivals */
 	long long n;
@@ -286,6 +287,7 @@ free_species(SpeciesHost &h)
 {
 	cudaFree(h.block);
 	cudaFree(h.oblock);
+	cudaFree(h.fblock);
 	cudaFree(h.pE);
 	double q = h.q, m = h.m;
 	memset(&h, 0, sizeof(h));
@@ -378,6 +380,16 @@ alloc_species(sim_t_ *s, int is, int cap)
 		ob.Ex = ob.Ey = NULL;
 	}
 	h.arr = 0;
+
+	CK(cudaMalloc(&h.fblock, (size_t) FAR_CAP * 8 * sizeof(double) + 256));
+	CK(cudaMemsetAsync(h.fblock, 0, (size_t) FAR_CAP * 8 * sizeof(double) + 256, s->stream));
+	{
+		double *f = (double *) h.fblock;
+		h.d.fx = f; h.d.fy = f + FAR_CAP; h.d.fux = f + 2 * FAR_CAP; h.d.fuy = f + 3 * FAR_CAP;
+		h.d.fuz = f + 4 * FAR_CAP; h.d.fEx = f + 5 * FAR_CAP; h.d.fEy = f + 6 * FAR_CAP;
+		h.d.fid = (long long *) (f + 7 * FAR_CAP);
+		h.d.fcount = (int *) (f + 8 * FAR_CAP);
+	}
 
 	if(s->p.keep_particle_E) return ensure_particle_E(s, is);
 	return 0;
@@ -732,14 +744,20 @@ cpic_b200_stage_plasma_E(cpic_b200_sim_t *s)
 static int
 exchange(sim_t_ *s)
 {
-	if(!s->comm) return 0;
 	StageTimer t(s, T_EXCHANGE);
 	for(int is = 0; is < s->p.nspecies; is++)
 	{
 		SpeciesHost &h = s->sp[is];
 		if(!h.block) continue;
-		int rc = comm_particles(s->comm, &h.d, h.arr, s->g, s->nb, s->stream, s->errflag, &s->launches);
+		/* particles that jumped further than a neighbouring block (normally none) */
+		k_far_insert<<<1, 1024, 0, s->stream>>>(h.d, s->g, s->errflag);
+		int rc = check_launch(s);
 		if(rc) return rc;
+		if(s->comm)
+		{
+			rc = comm_particles(s->comm, &h.d, h.arr, s->g, s->nb, s->stream, s->errflag, &s->launches);
+			if(rc) return rc;
+		}
 	}
 	return 0;
 }
@@ -908,7 +926,7 @@ cpic_b200_sync(cpic_b200_sim_t *s)
 	CK(cudaMemsetAsync(s->errflag, 0, sizeof(int), s->stream));
 	if(e & ERRBIT_TMA) return fail(CPIC_B200_ECUDA, "a TMA tile load did not complete (tensor map rejected)");
 	if(e & ERRBIT_VELOCITY) return fail(CPIC_B200_EVELOCITY, "Max velocity exceeded (umax = %g %g %g)", s->umax[0], s->umax[1], s->umax[2]);
-	if(e & ERRBIT_FAR) return fail(CPIC_B200_EFAR, "a particle crossed more than one particle block (%dx%d cells) in one step", s->g.BX, s->g.BY);
+	if(e & ERRBIT_FAR) return fail(CPIC_B200_EFAR, "a particle crossed a slab face by more than one particle block row (%d cells) in one step", s->g.BY);
 	return fail(CPIC_B200_ECAPACITY, "a particle block or outbox overflowed; raise capacity_factor (now %g)", s->p.capacity_factor);
 }
 

@@ -179,3 +179,29 @@ def test_empty_and_ragged_species():
         g.sync()
         assert_close(field_errors(g, o), what=f"ragged, iteration {it}")
         assert_close(particle_errors(g, o, p, with_E=True), what=f"ragged particles, iteration {it}")
+
+
+def test_far_movers():
+    """Particles that jump several particle blocks in one step (allowed by the reference up to
+    one chunk, src/sim.c:198-200) take the far-mover path and must still match the oracle."""
+    nx = ny = 64
+    n = 4000
+    rng = np.random.default_rng(11)
+    L = 8.0
+    dx = L / nx
+    dt = 0.05
+    p = Params(nx, ny, L, L, dt, 1.0e6, (0.0, 0.0, 0.1), (-1.0,), (1.0,), plasma_chunks=1)
+    v = 20.0 * dx / dt          # 20 cells per step: 2.5 blocks
+    parts = [{"id": np.arange(n), "x": rng.uniform(0, L, n), "y": rng.uniform(0, L, n),
+              "ux": np.where(np.arange(n) % 50 == 0, v, 0.1 * v / 20), "uy": np.where(np.arange(n) % 75 == 0, -v, 0.0)}]
+    o = oracle_from(p, parts)
+    g = gpu_from(p, parts)
+    o.pre_step()
+    g.pre_step()
+    for it in range(8):
+        g.step()
+        o.step()
+        g.sync()
+        assert g.num_particles(0) == n
+        assert_close(field_errors(g, o), what=f"far movers fields, iteration {it}")
+        assert_close(particle_errors(g, o, p), what=f"far movers particles, iteration {it}")
