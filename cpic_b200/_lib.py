@@ -56,6 +56,9 @@ EXPORTS = {
     "cpic_b200_comm_id": (_i, [_vp]),
     "cpic_b200_comm_init": (_i, [_vp, _vp]),
     "cpic_b200_set_particles": (_i, [_vp, _i, _i64] + [_vp] * 6),
+    "cpic_b200_capacity": (_i64, [_vp, _i]),
+    "cpic_b200_reserve": (_i, [_vp, _i, _i64]),
+    "cpic_b200_occupancy": (_i, [_vp, _i, C.POINTER(_i64 * 6)]),
     "cpic_b200_num_particles": (_i64, [_vp, _i]),
     "cpic_b200_get_particles": (_i64, [_vp, _i, _i64] + [_vp] * 8),
     "cpic_b200_init_uniform": (_i, [_vp, _i, _i64, _i64, _d, _d, C.c_uint64]),

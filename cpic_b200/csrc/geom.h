@@ -37,6 +37,9 @@
 #define ERRBIT_CAPACITY 2
 #define ERRBIT_FAR 4
 #define ERRBIT_TMA 8
+#define ERRBIT_REGION 16      /* an exchange region overflowed */
+#define ERRBIT_FARLIST 32     /* more far movers in one step than the list holds */
+#define ERRBIT_ABSORB 64      /* a block could not take its arrivals */
 
 /* One rank's slab and its decomposition into particle blocks of BX x BY cells */
 struct Geom {

@@ -300,16 +300,21 @@ cpic_b200_sim_from_conf(const char *path, int rank, int nranks, int device, int 
 			continue;
 		}
 		std::vector<int64_t> sid; std::vector<double> sx, sy, sux, suy;
+		std::vector<size_t> per_rank((size_t) nranks, 0);
 		for(size_t i = 0; i < n; i++)
 		{
 			long long row = (long long) floor(py[is][i] * (1.0 / dy));
 			if(row < 0) row = 0;
 			if(row > p.ny - 1) row = p.ny - 1;
+			per_rank[(size_t) (row / rows)]++;
 			if(row / rows != rank) continue;
 			sid.push_back(pid[is][i]); sx.push_back(px[is][i]); sy.push_back(py[is][i]);
 			sux.push_back(pux[is][i]); suy.push_back(puy[is][i]);
 		}
 		rc = cpic_b200_set_particles(sim, is, (int64_t) sid.size(), sid.data(), sx.data(), sy.data(), sux.data(), suy.data(), NULL);
+		/* every rank sees the whole population here, but only bins its own slab: the common
+		 * block capacity is agreed by the caller (cpic_b200_capacity / cpic_b200_reserve) */
+		(void) per_rank;
 	}
 	if(!rc && nranks == 1) rc = cpic_b200_pre_step(sim);
 	if(rc) { cpic_b200_destroy(sim); return rc; }

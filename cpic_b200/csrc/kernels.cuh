@@ -55,10 +55,12 @@ struct SpeciesDev {
 	 * list, inserted by k_far_insert in id order */
 	double *fx, *fy, *fux, *fuy, *fuz, *fEx, *fEy;
 	long long *fid;
+	long long *fkey;         /* sort scratch: (destination block, id) */
+	int *fidx;
 	int *fcount;
 };
 
-#define FAR_CAP 2048
+#define FAR_CAP 65536
 
 /* Slot of entry `pos` in the region (block b, destination code c) */
 __device__ __forceinline__ unsigned
@@ -592,7 +594,7 @@ k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 						sp.fid[k] = pid;
 						sp.fEx[k] = Ex; sp.fEy[k] = Ey;
 					}
-					else bad |= 2;
+					else bad |= 16;
 				}
 				else if(pos < sp.rcap[dest])
 				{
@@ -602,7 +604,7 @@ k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 					out.id[o] = pid;
 					if(out.Ex) { out.Ex[o] = Ex; out.Ey[o] = Ey; }
 				}
-				else bad |= 2;
+				else bad |= 8;
 			}
 			__syncwarp();
 		}
@@ -625,32 +627,25 @@ k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 			if(bad & 1) bits |= ERRBIT_VELOCITY;
 			if(bad & 2) bits |= ERRBIT_CAPACITY;
 			if(bad & 4) bits |= ERRBIT_FAR;
+			if(bad & 8) bits |= ERRBIT_REGION;
+			if(bad & 16) bits |= ERRBIT_FARLIST;
 			atomicOr(errflag, bits);
 		}
 	}
 }
 
-/* Far movers: the list filled by the push (in arbitrary order) is sorted by particle id
- * by one CTA (bitonic sort in shared memory) and appended to the destination blocks'
- * segments one by one, so the result does not depend on the order of arrival. A
- * destination outside this rank's slab is an error (the reference bounds a step to one
- * chunk, src/sim.c:198-200; here the bound across a slab face is one block row). */
-static __global__ void __launch_bounds__(1024)
-k_far_insert(SpeciesDev sp, Geom g, int *__restrict__ errflag)
+/* Far movers: the list filled by the push (in arbitrary order) is sorted by (destination
+ * block, particle id) by one CTA -- a bitonic sort, in shared memory when the list is
+ * short, in global scratch otherwise -- and every block's run is appended to its segment
+ * in that order, so the result does not depend on the order of arrival. A destination
+ * outside this rank's slab is an error (the reference bounds a step to one chunk,
+ * src/sim.c:198-200; here the bound across a slab face is one block row). */
+#define FAR_SMEM 2048
+
+template <typename K, typename I>
+__device__ __forceinline__ void
+bitonic_sort(K *key, I *idx, int m)
 {
-	__shared__ long long key[FAR_CAP];
-	__shared__ int idx[FAR_CAP];
-	int n = *sp.fcount;
-	if(n == 0) return;
-	if(n > FAR_CAP) n = FAR_CAP;
-	int m = 1;
-	while(m < n) m <<= 1;
-	for(int i = threadIdx.x; i < m; i += blockDim.x)
-	{
-		key[i] = i < n ? sp.fid[i] : 0x7fffffffffffffffLL;
-		idx[i] = i;
-	}
-	__syncthreads();
 	for(int k = 2; k <= m; k <<= 1)
 		for(int j = k >> 1; j > 0; j >>= 1)
 		{
@@ -660,35 +655,106 @@ k_far_insert(SpeciesDev sp, Geom g, int *__restrict__ errflag)
 				if(l > i)
 				{
 					const bool up = (i & k) == 0;
-					if((key[i] > key[l]) == up)
+					const K a = key[i], b = key[l];
+					if((a > b) == up)
 					{
-						const long long tk = key[i]; key[i] = key[l]; key[l] = tk;
-						const int ti = idx[i]; idx[i] = idx[l]; idx[l] = ti;
+						key[i] = b; key[l] = a;
+						const I t = idx[i]; idx[i] = idx[l]; idx[l] = t;
 					}
 				}
 			}
 			__syncthreads();
 		}
-	if(threadIdx.x == 0)
+}
+
+static __global__ void __launch_bounds__(1024)
+k_far_insert(SpeciesDev sp, Geom g, int *__restrict__ errflag)
+{
+	__shared__ long long skey[FAR_SMEM];
+	__shared__ int sidx[FAR_SMEM];
+	int n = *sp.fcount;
+	if(n == 0) return;
+	if(n > FAR_CAP) n = FAR_CAP;
+	int m = 1;
+	while(m < n) m <<= 1;
+	long long *key = m <= FAR_SMEM ? skey : sp.fkey;
+	int *idx = m <= FAR_SMEM ? sidx : sp.fidx;
+	const long long OUT = 0x7ffffffffffffffeLL, PAD = 0x7fffffffffffffffLL;
+	for(int i = threadIdx.x; i < m; i += blockDim.x)
 	{
-		for(int j = 0; j < n; j++)
+		long long k = PAD;
+		if(i < n)
 		{
-			const int e = idx[j];
-			const double x = sp.fx[e], y = sp.fy[e];
+			const double x = sp.fx[i], y = sp.fy[i];
 			const int row = global_row(g, y);
-			if(row < g.row0 || row >= g.row0 + g.ny) { atomicOr(errflag, ERRBIT_FAR); continue; }
-			const int b = block_of(g, x, y);
-			const int pos = sp.count[b];
-			if(pos >= sp.cap) { atomicOr(errflag, ERRBIT_CAPACITY); continue; }
+			if(row < g.row0 || row >= g.row0 + g.ny) { k = OUT; atomicOr(errflag, ERRBIT_FAR); }
+			else k = ((long long) block_of(g, x, y) << 40) | (sp.fid[i] & 0xffffffffffLL);
+		}
+		key[i] = k;
+		idx[i] = i;
+	}
+	__syncthreads();
+	bitonic_sort(key, idx, m);
+	/* the first entry of every block's run appends the whole run */
+	for(int i = threadIdx.x; i < n; i += blockDim.x)
+	{
+		const long long k = key[i];
+		if(k >= OUT) continue;
+		const int b = (int) (k >> 40);
+		if(i > 0 && (int) (key[i - 1] >> 40) == b) continue;
+		int pos = sp.count[b];
+		for(int j = i; j < n && (int) (key[j] >> 40) == b && key[j] < OUT; j++)
+		{
+			if(pos >= sp.cap) { atomicOr(errflag, ERRBIT_ABSORB); break; }
+			const int e = idx[j];
 			const size_t d = (size_t) b * sp.cap + pos;
-			sp.x[d] = x; sp.y[d] = y;
+			sp.x[d] = sp.fx[e]; sp.y[d] = sp.fy[e];
 			sp.ux[d] = sp.fux[e]; sp.uy[d] = sp.fuy[e]; sp.uz[d] = sp.fuz[e];
 			sp.id[d] = sp.fid[e];
 			if(sp.pEx) { sp.pEx[d] = sp.fEx[e]; sp.pEy[d] = sp.fEy[e]; }
-			sp.count[b] = pos + 1;
+			pos++;
 		}
-		*sp.fcount = 0;
+		sp.count[b] = pos;
 	}
+	__syncthreads();
+	if(threadIdx.x == 0) *sp.fcount = 0;
+}
+
+/* Moves every block's particles (own segment, then pending arrivals) into a species laid
+ * out with a larger capacity `dst`. Not on the per-step path: capacity management only. */
+static __global__ void __launch_bounds__(256)
+k_regrow(SpeciesDev sp, SpeciesDev dst, Geom g, int nb, int arr)
+{
+	__shared__ int scratch[8][18];
+	const int lane = threadIdx.x & 31;
+	const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	if(b >= nb) return;
+	const Outbox &in = sp.ob[arr];
+	const Arrivals A = find_arrivals(in, sp.nob, g, nb, b, lane, scratch[threadIdx.x >> 5]);
+	const int cnt = sp.count[b];
+	const size_t base = (size_t) b * sp.cap, dbase = (size_t) b * dst.cap;
+	for(int i = lane; i < cnt + A.total; i += 32)
+	{
+		const size_t d = dbase + i;
+		if(i >= dst.cap) break;
+		if(i < cnt)
+		{
+			const size_t s = base + i;
+			dst.x[d] = sp.x[s]; dst.y[d] = sp.y[s];
+			dst.ux[d] = sp.ux[s]; dst.uy[d] = sp.uy[s]; dst.uz[d] = sp.uz[s];
+			dst.id[d] = sp.id[s];
+			if(dst.pEx && sp.pEx) { dst.pEx[d] = sp.pEx[s]; dst.pEy[d] = sp.pEy[s]; }
+		}
+		else
+		{
+			const size_t s = arrival_slot(A, sp, i - cnt);
+			dst.x[d] = in.x[s]; dst.y[d] = in.y[s];
+			dst.ux[d] = in.ux[s]; dst.uy[d] = in.uy[s]; dst.uz[d] = in.uz[s];
+			dst.id[d] = in.id[s];
+			if(dst.pEx && in.Ex) { dst.pEx[d] = in.Ex[s]; dst.pEy[d] = in.Ey[s]; }
+		}
+	}
+	if(lane == 0) dst.count[b] = min(cnt + A.total, dst.cap);
 }
 
 /* Appends the pending arrivals of every block (outbox `arr`) to its own segment and
@@ -708,7 +774,7 @@ k_absorb(SpeciesDev sp, Geom g, int nb, int arr, int *__restrict__ errflag)
 	const size_t base = (size_t) b * sp.cap;
 	if(cnt + A.total > sp.cap)
 	{
-		if(lane == 0) atomicOr(errflag, ERRBIT_CAPACITY);
+		if(lane == 0) atomicOr(errflag, ERRBIT_ABSORB);
 		return;
 	}
 	for(int f = lane; f < A.total; f += 32)

@@ -51,6 +51,7 @@ struct SpeciesHost {
 	size_t block_bytes;
 	void *oblock;            /* the two outboxes */
 	void *fblock;            /* far-mover list */
+	int reserve;             /* floor for the block capacity (cpic_b200_reserve) */
 	double *pE;              /* optional per-particle E (segment and outboxes) */
 	int arr;                 /* outbox that holds the pending arrivals */
 	long long n;
@@ -290,8 +291,9 @@ free_species(SpeciesHost &h)
 	cudaFree(h.fblock);
 	cudaFree(h.pE);
 	double q = h.q, m = h.m;
+	int reserve = h.reserve;
 	memset(&h, 0, sizeof(h));
-	h.q = q; h.m = m;
+	h.q = q; h.m = m; h.reserve = reserve;
 }
 
 extern "C" void
@@ -381,14 +383,16 @@ alloc_species(sim_t_ *s, int is, int cap)
 	}
 	h.arr = 0;
 
-	CK(cudaMalloc(&h.fblock, (size_t) FAR_CAP * 8 * sizeof(double) + 256));
-	CK(cudaMemsetAsync(h.fblock, 0, (size_t) FAR_CAP * 8 * sizeof(double) + 256, s->stream));
+	CK(cudaMalloc(&h.fblock, (size_t) FAR_CAP * 10 * sizeof(double) + 256));
+	CK(cudaMemsetAsync(h.fblock, 0, (size_t) FAR_CAP * 10 * sizeof(double) + 256, s->stream));
 	{
 		double *f = (double *) h.fblock;
 		h.d.fx = f; h.d.fy = f + FAR_CAP; h.d.fux = f + 2 * FAR_CAP; h.d.fuy = f + 3 * FAR_CAP;
 		h.d.fuz = f + 4 * FAR_CAP; h.d.fEx = f + 5 * FAR_CAP; h.d.fEy = f + 6 * FAR_CAP;
 		h.d.fid = (long long *) (f + 7 * FAR_CAP);
-		h.d.fcount = (int *) (f + 8 * FAR_CAP);
+		h.d.fkey = (long long *) (f + 8 * FAR_CAP);
+		h.d.fidx = (int *) (f + 9 * FAR_CAP);
+		h.d.fcount = (int *) (f + 10 * FAR_CAP);
 	}
 
 	if(s->p.keep_particle_E) return ensure_particle_E(s, is);
@@ -454,7 +458,8 @@ cpic_b200_set_particles(cpic_b200_sim_t *s, int is, int64_t n, const int64_t *id
 	int cap = cap_for(s, std::max<long long>(maxc, mean));
 
 	SpeciesHost &h = s->sp[is];
-	if(!h.block || h.d.cap < cap)
+	if(cap < h.reserve) cap = h.reserve;
+	if(!h.block || h.d.cap != cap)
 	{
 		int rc = alloc_species(s, is, cap);
 		if(rc) return rc;
@@ -494,7 +499,8 @@ cpic_b200_init_uniform(cpic_b200_sim_t *s, int is, int64_t n, int64_t id0, doubl
 	long long per = (n + s->nb - 1) / s->nb;
 	int cap = cap_for(s, per);
 	SpeciesHost &h = s->sp[is];
-	if(!h.block || h.d.cap < cap)
+	if(cap < h.reserve) cap = h.reserve;
+	if(!h.block || h.d.cap != cap)
 	{
 		int rc = alloc_species(s, is, cap);
 		if(rc) return rc;
@@ -503,6 +509,114 @@ cpic_b200_init_uniform(cpic_b200_sim_t *s, int is, int64_t n, int64_t id0, doubl
 	CK(cudaGetLastError());
 	for(int k = 0; k < 2; k++) CK(cudaMemsetAsync(h.d.ob[k].count, 0, (size_t) s->nob * 9 * sizeof(int), s->stream));
 	h.n = n;
+	return 0;
+}
+
+/* Host view of the fill of one species: counts of the segments and of the regions that hold
+ * pending arrivals */
+static int
+occupancy(sim_t_ *s, int is, int64_t out[6])
+{
+	SpeciesHost &h = s->sp[is];
+	memset(out, 0, 6 * sizeof(int64_t));
+	if(!h.block) return 0;
+	std::vector<int> cnt((size_t) s->nb), oc((size_t) s->nob * 9);
+	CK(cudaMemcpyAsync(cnt.data(), h.d.count, cnt.size() * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+	CK(cudaMemcpyAsync(oc.data(), h.d.ob[h.arr].count, oc.size() * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+	CK(cudaStreamSynchronize(s->stream));
+	/* a block's next segment can hold everything it has now plus what is on its way */
+	int64_t mb = 0, ms = 0, mc = 0;
+	for(int b = 0; b < s->nb; b++) mb = std::max<int64_t>(mb, cnt[(size_t) b]);
+	int64_t pending = 0;
+	for(int c = 0; c < 9; c++)
+	{
+		if(c == DEST_STAY) continue;
+		for(int b = 0; b < s->nob; b++)
+		{
+			const int v = oc[(size_t) c * s->nob + b];
+			pending = std::max<int64_t>(pending, v);
+			if(c & 1) ms = std::max<int64_t>(ms, v); else mc = std::max<int64_t>(mc, v);
+		}
+	}
+	out[0] = mb + 2 * ms + mc; out[1] = h.d.cap;
+	out[2] = ms; out[3] = h.d.ocs;
+	out[4] = mc; out[5] = h.d.occ;
+	(void) pending;
+	return 0;
+}
+
+extern "C" int
+cpic_b200_occupancy(cpic_b200_sim_t *s, int is, int64_t out[6])
+{
+	if(!s || !out || is < 0 || is >= s->p.nspecies) return fail(CPIC_B200_EINVAL, "bad argument");
+	CK(cudaSetDevice(s->device));
+	return occupancy(s, is, out);
+}
+
+static int alloc_species(sim_t_ *s, int is, int cap);
+
+/* Re-lays a species out with `newcap` slots per block (and exchange regions in proportion) */
+static int
+regrow(sim_t_ *s, int is, int newcap)
+{
+	SpeciesHost old = s->sp[is];
+	SpeciesHost &h = s->sp[is];
+	const bool hadE = old.d.pEx != NULL;
+	/* detach the old storage so that alloc_species does not free it */
+	h.block = h.oblock = h.fblock = NULL;
+	h.pE = NULL;
+	memset(&h.d, 0, sizeof(h.d));
+	int rc = alloc_species(s, is, newcap);
+	if(!rc && hadE && !h.d.pEx) rc = ensure_particle_E(s, is);
+	if(rc) return rc;
+	k_regrow<<<(s->nb + 7) / 8, 256, 0, s->stream>>>(old.d, h.d, s->g, s->nb, old.arr);
+	CK(cudaGetLastError());
+	CK(cudaStreamSynchronize(s->stream));
+	h.n = old.n;
+	cudaFree(old.block); cudaFree(old.oblock); cudaFree(old.fblock); cudaFree(old.pE);
+	return 0;
+}
+
+/* Grows the storage of any species that runs above 80 % of its block or region capacity.
+ * Collective decisions are not needed on one rank; with several ranks the capacities must
+ * stay equal, so growth there is left to the caller (cpic_b200_reserve). */
+static int
+check_capacity(sim_t_ *s)
+{
+	if(s->comm) return 0;
+	for(int is = 0; is < s->p.nspecies; is++)
+	{
+		int64_t o[6];
+		int rc = occupancy(s, is, o);
+		if(rc) return rc;
+		if(!o[1]) continue;
+		const bool tight = o[0] * 10 > o[1] * 8 || o[2] * 10 > o[3] * 8 || o[4] * 10 > o[5] * 8;
+		if(!tight) continue;
+		int64_t want = std::max<int64_t>(o[1] * 3 / 2, o[0] * 2);
+		/* regions scale with the block capacity; make sure they clear the observed peaks */
+		const double frac = s->p.outbox_fraction > 0 ? s->p.outbox_fraction : 0.3;
+		want = std::max<int64_t>(want, (int64_t) (2.0 * o[2] / frac));
+		want = std::max<int64_t>(want, (int64_t) (8.0 * o[4] / frac));
+		want = (want + 31) / 32 * 32;
+		rc = regrow(s, is, (int) std::min<int64_t>(want, 1 << 30));
+		if(rc) return rc;
+	}
+	return 0;
+}
+
+extern "C" int64_t
+cpic_b200_capacity(cpic_b200_sim_t *s, int is)
+{
+	if(!s || is < 0 || is >= s->p.nspecies) return -1;
+	return s->sp[is].block ? s->sp[is].d.cap : 0;
+}
+
+extern "C" int
+cpic_b200_reserve(cpic_b200_sim_t *s, int is, int64_t capacity)
+{
+	if(!s || is < 0 || is >= s->p.nspecies || capacity < 0 || capacity > (1 << 30))
+		return fail(CPIC_B200_EINVAL, "bad species or capacity");
+	s->sp[is].reserve = (int) ((capacity + 31) / 32 * 32);
 	return 0;
 }
 
@@ -875,6 +989,7 @@ cpic_b200_run(cpic_b200_sim_t *s, int64_t steps)
 	for(int64_t i = 0; i < steps; i++)
 	{
 		int rc = cpic_b200_step(s);
+		if(!rc && (i & 31) == 31) rc = check_capacity(s);
 		if(rc) return rc;
 	}
 	return cpic_b200_sync(s);
@@ -892,7 +1007,11 @@ cpic_b200_run_timed(cpic_b200_sim_t *s, int64_t steps, double *ms)
 	CK(cudaStreamSynchronize(s->stream));
 	CK(cudaEventRecord(a, s->stream));
 	int rc = 0;
-	for(int64_t i = 0; i < steps && !rc; i++) rc = cpic_b200_step(s);
+	for(int64_t i = 0; i < steps && !rc; i++)
+	{
+		rc = cpic_b200_step(s);
+		if(!rc && (i & 31) == 31) rc = check_capacity(s);
+	}
 	CK(cudaEventRecord(b, s->stream));
 	CK(cudaEventSynchronize(b));
 	float t = 0;
@@ -922,12 +1041,15 @@ cpic_b200_sync(cpic_b200_sim_t *s)
 	CK(cudaMemcpyAsync(s->h_err, s->errflag, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
 	CK(cudaStreamSynchronize(s->stream));
 	const int e = *s->h_err;
-	if(!e) return 0;
+	if(!e) return check_capacity(s);
 	CK(cudaMemsetAsync(s->errflag, 0, sizeof(int), s->stream));
 	if(e & ERRBIT_TMA) return fail(CPIC_B200_ECUDA, "a TMA tile load did not complete (tensor map rejected)");
 	if(e & ERRBIT_VELOCITY) return fail(CPIC_B200_EVELOCITY, "Max velocity exceeded (umax = %g %g %g)", s->umax[0], s->umax[1], s->umax[2]);
 	if(e & ERRBIT_FAR) return fail(CPIC_B200_EFAR, "a particle crossed a slab face by more than one particle block row (%d cells) in one step", s->g.BY);
-	return fail(CPIC_B200_ECAPACITY, "a particle block or outbox overflowed; raise capacity_factor (now %g)", s->p.capacity_factor);
+	return fail(CPIC_B200_ECAPACITY, "capacity exceeded (%s%s%s%s): raise capacity_factor (now %g) / outbox_fraction",
+			(e & ERRBIT_CAPACITY) ? "particle block segment " : "", (e & ERRBIT_REGION) ? "exchange region " : "",
+			(e & ERRBIT_FARLIST) ? "far-mover list " : "", (e & ERRBIT_ABSORB) ? "arrivals do not fit " : "",
+			s->p.capacity_factor);
 }
 
 /* ------------------------------------------------------------------ fields */

@@ -44,3 +44,16 @@ def bootstrap(sim, dist, device=None):
     """ncclCommInitRank on every rank with rank 0's unique id."""
     ident = sim.comm_id() if dist.get_rank() == 0 else bytes(128)
     sim.comm_init(broadcast_id(ident, dist, device))
+
+
+def set_particles_collective(sim, parts, dist, device=None):
+    """set_particles on every rank with one block capacity for all of them (the particle
+    exchange buffers are sized from it, so the ranks must agree)."""
+    import torch
+    for i, p in enumerate(parts):
+        sim.set_particles(i, p["id"], p["x"], p["y"], p["ux"], p["uy"], p.get("uz"))
+        cap = torch.tensor([sim.capacity(i)], dtype=torch.int64, device=device)
+        dist.all_reduce(cap, op=dist.ReduceOp.MAX)
+        if int(cap.item()) != sim.capacity(i):
+            sim.reserve(i, int(cap.item()))
+            sim.set_particles(i, p["id"], p["x"], p["y"], p["ux"], p["uy"], p.get("uz"))

@@ -165,6 +165,17 @@ class Sim:
         uz = None if uz is None else np.ascontiguousarray(uz, np.float64)
         check(self.L.cpic_b200_set_particles(self.h, species, len(a[0]), *[_ptr(v) for v in a], _ptr(uz)))
 
+    def capacity(self, species):
+        return self.L.cpic_b200_capacity(self.h, species)
+
+    def occupancy(self, species):
+        o = (C.c_int64 * 6)()
+        check(self.L.cpic_b200_occupancy(self.h, species, C.byref(o)))
+        return dict(zip(("block", "block_cap", "side", "side_cap", "corner", "corner_cap"), o))
+
+    def reserve(self, species, capacity):
+        check(self.L.cpic_b200_reserve(self.h, species, capacity))
+
     def init_uniform(self, species, n, id0=0, vx=0.0, vy=0.0, seed=138):
         check(self.L.cpic_b200_init_uniform(self.h, species, n, id0, vx, vy, seed))
 

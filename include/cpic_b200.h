@@ -83,6 +83,16 @@ int cpic_b200_comm_init(cpic_b200_sim_t *sim, const void *id128);
 int cpic_b200_set_particles(cpic_b200_sim_t *sim, int species, int64_t n,
 		const int64_t *id, const double *x, const double *y,
 		const double *ux, const double *uy, const double *uz);
+/* Block capacity (slots per particle block) of a species. With several ranks every rank must
+ * use the same capacity (the exchange buffers are sized from it): set_particles on every
+ * rank, take the maximum of cpic_b200_capacity over the ranks, and if it differs from the
+ * local value call cpic_b200_reserve with it and set_particles again. */
+int64_t cpic_b200_capacity(cpic_b200_sim_t *sim, int species);
+int cpic_b200_reserve(cpic_b200_sim_t *sim, int species, int64_t capacity);
+/* Fill of the fullest particle block and exchange regions of a species, next to their
+ * capacities: out[6] = { max block count, block capacity, max side-region count, side
+ * capacity, max corner-region count, corner capacity }. */
+int cpic_b200_occupancy(cpic_b200_sim_t *sim, int species, int64_t out[6]);
 int64_t cpic_b200_num_particles(cpic_b200_sim_t *sim, int species);
 /* Host SoA out, in device (particle-block) order; any pointer may be NULL.
  * Ex/Ey are the fields last gathered onto the particles (ppack.E, src/def.h:96).

@@ -14,7 +14,7 @@ import torch
 import torch.distributed as dist
 
 from cpic_b200 import Sim, load_conf, init_particles
-from cpic_b200.dist import env_rank, partition, bootstrap
+from cpic_b200.dist import env_rank, partition, bootstrap, set_particles_collective
 from _parity import oracle_from, relerr, TOL
 
 
@@ -28,8 +28,7 @@ def main():
     parts = init_particles(conf)
     o = oracle_from(params, parts)
     g = Sim(params)
-    for i, p in enumerate(partition(parts, params, rank)):
-        g.set_particles(i, p["id"], p["x"], p["y"], p["ux"], p["uy"])
+    set_particles_collective(g, partition(parts, params, rank), dist, device="cuda")
     bootstrap(g, dist, device="cuda")
     o.pre_step()
     g.pre_step()
