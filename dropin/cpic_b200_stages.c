@@ -1,0 +1,192 @@
+/* Reference-side binding of cpic_b200: the four stage functions of cpic's sim_step
+ * (src/sim.c:503,517,525,536) with their original signatures, implemented over the C ABI of
+ * include/cpic_b200.h. A cpic maintainer adds this one file to src/, drops the bodies of
+ * stage_field_E / stage_field_rho (src/field.c:268-356,450-501), stage_plasma_E
+ * (src/particle.c:232-248) and stage_plasma_r (src/mover.c:331-362), and links
+ * libcpic_b200.so; sim.c, cpic.c, the .conf handling, plasma_init and the test drivers stay
+ * as they are. It is compiled against the reference's own headers (never copied here).
+ *
+ * Host/device coherence: the particles and grids live on the GPU between stages. The host
+ * structures the reference's drivers read after a step (`chunks[ic].species[is].list.b->p[..]`
+ * in test/cyclotron.c:65-73, test/harmonic.c:40-55; `sim->field._rho/_phi/_E` in
+ * src/output.c:627-630) are refreshed at the end of stage_field_rho, the last stage of a
+ * step, unless CPIC_B200_SYNC=lazy is set, in which case cpic_b200_dropin_sync(sim) does
+ * it on demand.
+ */
+#define _GNU_SOURCE
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "sim.h"
+#include "field.h"
+#include "particle.h"
+#include "mover.h"
+#include "perf.h"
+
+#include "cpic_b200.h"
+
+typedef struct slot { ppack_t *p; int lane; } slot_t;
+
+static struct {
+	sim_t *sim;
+	cpic_b200_sim_t *gpu;
+	slot_t **slots;          /* per species: id -> host slot */
+	int lazy;
+} D;
+
+static void
+fatal(const char *what)
+{
+	/* the reference's convention for unrecoverable errors (src/log.h:69-70) */
+	fprintf(stderr, "cpic_b200: %s: %s\n", what, cpic_b200_last_error());
+	abort();
+}
+
+/* plist -> SoA upload (after plasma_init and particle_comm_initial have run on the host) */
+static void
+attach(sim_t *sim)
+{
+	cpic_b200_params_t p;
+	i64 is, ic;
+
+	if(D.gpu) return;
+	memset(&p, 0, sizeof(p));
+	p.nx = sim->ntpoints[X];
+	p.ny = sim->ntpoints[Y];
+	p.Lx = sim->L[X];
+	p.Ly = sim->L[Y];
+	p.dt = sim->dt;
+	p.e0 = sim->e0;
+	p.B[0] = sim->B[X]; p.B[1] = sim->B[Y]; p.B[2] = sim->B[Z];
+	p.plasma_chunks = sim->plasma_chunks;
+	p.nspecies = (int) sim->nspecies;
+	for(is = 0; is < sim->nspecies; is++) { p.q[is] = sim->species[is].q; p.m[is] = sim->species[is].m; }
+	p.rank = sim->rank;
+	p.nranks = sim->nprocs;
+	p.device = -1;
+	p.keep_particle_E = 1;   /* ppack.E is part of the host structure the drivers read */
+	if(cpic_b200_create(&p, &D.gpu)) fatal("create");
+	D.sim = sim;
+	D.lazy = getenv("CPIC_B200_SYNC") && strcmp(getenv("CPIC_B200_SYNC"), "lazy") == 0;
+	D.slots = calloc((size_t) sim->nspecies, sizeof(slot_t *));
+
+	for(is = 0; is < sim->nspecies; is++)
+	{
+		i64 n = 0, k = 0, ip, iv, nmax = sim->species[is].nparticles;
+		i64 *id = malloc((size_t) nmax * sizeof(i64));
+		double *x = malloc((size_t) nmax * sizeof(double)), *y = malloc((size_t) nmax * sizeof(double));
+		double *ux = malloc((size_t) nmax * sizeof(double)), *uy = malloc((size_t) nmax * sizeof(double));
+		double *uz = malloc((size_t) nmax * sizeof(double));
+		D.slots[is] = calloc((size_t) nmax, sizeof(slot_t));
+		for(ic = 0; ic < sim->plasma.nchunks; ic++)
+		{
+			pblock_t *b;
+			for(b = sim->plasma.chunks[ic].species[is].list.b; b; b = b->next)
+				for(ip = 0; ip < b->npacks; ip++)
+					for(iv = 0; iv < MAX_VEC && ip * MAX_VEC + iv < b->n; iv++)
+					{
+						ppack_t *pk = &b->p[ip];
+						if(k >= nmax) fatal("more particles in the lists than the species declares");
+						id[k] = pk->i[iv];
+						x[k] = pk->r[X][iv]; y[k] = pk->r[Y][iv];
+						ux[k] = pk->u[X][iv]; uy[k] = pk->u[Y][iv]; uz[k] = pk->u[Z][iv];
+						D.slots[is][pk->i[iv]].p = pk;
+						D.slots[is][pk->i[iv]].lane = (int) iv;
+						k++;
+					}
+		}
+		n = k;
+		if(cpic_b200_set_particles(D.gpu, (int) is, n, (const int64_t *) id, x, y, ux, uy, uz)) fatal("set_particles");
+		free(id); free(x); free(y); free(ux); free(uy); free(uz);
+	}
+}
+
+/* grids -> mat_t */
+static void
+sync_fields(sim_t *sim)
+{
+	field_t *f = &sim->field;
+	int64_t rows, stride;
+	/* same strides as the reference's padded arrays (src/field.c:20-160) */
+	if(cpic_b200_field_shape(D.gpu, CPIC_B200_RHO, &rows, &stride) || stride != f->_rho->real_shape[X])
+		fatal("rho stride differs from the reference layout");
+	if(cpic_b200_get_field(D.gpu, CPIC_B200_RHO, f->_rho->data)) fatal("get rho");
+	if(cpic_b200_get_field(D.gpu, CPIC_B200_PHI, f->_phi->data)) fatal("get phi");
+	if(cpic_b200_get_field(D.gpu, CPIC_B200_EX, f->_E[X]->data)) fatal("get E_X");
+	if(cpic_b200_get_field(D.gpu, CPIC_B200_EY, f->_E[Y]->data)) fatal("get E_Y");
+}
+
+/* SoA -> plist (by particle id) and grids -> mat_t */
+void
+cpic_b200_dropin_sync(sim_t *sim)
+{
+	i64 is, k;
+
+	if(!D.gpu) return;
+	for(is = 0; is < sim->nspecies; is++)
+	{
+		i64 nmax = sim->species[is].nparticles, n;
+		i64 *id = malloc((size_t) nmax * sizeof(i64));
+		double *a[7];
+		for(k = 0; k < 7; k++) a[k] = malloc((size_t) nmax * sizeof(double));
+		n = cpic_b200_get_particles(D.gpu, (int) is, nmax, (int64_t *) id, a[0], a[1], a[2], a[3], a[4], a[5], a[6]);
+		if(n < 0 || n > nmax) fatal("get_particles");
+		for(k = 0; k < n; k++)
+		{
+			slot_t s = D.slots[is][id[k]];
+			s.p->r[X][s.lane] = a[0][k]; s.p->r[Y][s.lane] = a[1][k];
+			s.p->u[X][s.lane] = a[2][k]; s.p->u[Y][s.lane] = a[3][k]; s.p->u[Z][s.lane] = a[4][k];
+			s.p->E[X][s.lane] = a[5][k]; s.p->E[Y][s.lane] = a[6][k];
+		}
+		free(id);
+		for(k = 0; k < 7; k++) free(a[k]);
+	}
+	sync_fields(sim);
+}
+
+int
+stage_field_E(sim_t *sim)
+{
+	attach(sim);
+	perf_start(&sim->timers[TIMER_FIELD_E]);
+	cpic_b200_set_iter(D.gpu, sim->iter);
+	if(cpic_b200_stage_field_E(D.gpu)) fatal("stage_field_E");
+	/* output_fields runs right after this stage (src/sim.c:507) and reads the host grids */
+	if(!D.lazy && sim->output && sim->output->enabled) sync_fields(sim);
+	perf_stop(&sim->timers[TIMER_FIELD_E]);
+	return 0;
+}
+
+void
+stage_plasma_E(sim_t *sim)
+{
+	attach(sim);
+	perf_start(&sim->timers[TIMER_PARTICLE_E]);
+	cpic_b200_set_iter(D.gpu, sim->iter);
+	if(cpic_b200_stage_plasma_E(D.gpu)) fatal("stage_plasma_E");
+	perf_stop(&sim->timers[TIMER_PARTICLE_E]);
+}
+
+void
+stage_plasma_r(sim_t *sim)
+{
+	attach(sim);
+	perf_start(&sim->timers[TIMER_PARTICLE_X]);
+	cpic_b200_set_iter(D.gpu, sim->iter);
+	if(cpic_b200_stage_plasma_r(D.gpu)) fatal("stage_plasma_r");
+	perf_stop(&sim->timers[TIMER_PARTICLE_X]);
+}
+
+void
+stage_field_rho(sim_t *sim)
+{
+	attach(sim);
+	perf_start(&sim->timers[TIMER_FIELD_RHO]);
+	cpic_b200_set_iter(D.gpu, sim->iter);
+	if(cpic_b200_stage_field_rho(D.gpu)) fatal("stage_field_rho");
+	/* velocity limit etc. surface here, where the reference would have aborted */
+	if(cpic_b200_sync(D.gpu)) fatal("step");
+	if(!D.lazy) cpic_b200_dropin_sync(sim);
+	perf_stop(&sim->timers[TIMER_FIELD_RHO]);
+}

@@ -1,0 +1,92 @@
+"""Drop-in: the reference's own drivers (src/cpic.c main and test/cyclotron.c,
+test/constant-speed.c, test/harmonic.c), built from /root/reference by `make -C oracle dropin`
+with their four stage functions bound to libcpic_b200.so (dropin/cpic_b200_stages.c), run on
+the GPU. The binaries travel in oracle/_ref/ (the reference tree does not exist on the GPU box)."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+REF = os.path.join(ROOT, "oracle", "_ref")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def run(binary, *args, timeout=600):
+    path = os.path.join(REF, binary)
+    if not os.path.exists(path):
+        pytest.skip(f"{binary} not built (needs /root/reference at build time)")
+    # the drivers open conf/<name>.conf relative to the working directory: the repo's confs
+    return subprocess.run([path, *args], cwd=ROOT, capture_output=True, text=True, timeout=timeout)
+
+
+def test_reference_cyclotron_driver():
+    """test/cyclotron.c prints the largest deviation from R(cos wt, sin wt) over its 5000 cycles
+    (:317-326). Over the full run the Boris phase error alone (n (w dt)^3 / 24 = 0.026 rad on a
+    radius of 10) exceeds the driver's limit v*dt^2 on the CPU reference too, so the check is
+    that the GPU-backed driver reports the same deviation as the CPU-backed one."""
+    g = run("dropin_cyclotron.test")
+    c = run("ref_cyclotron.test")
+    num = lambda r: float(re.search(r"rror ([0-9.e+-]+)", r.stdout).group(1))
+    assert g.returncode == c.returncode
+    assert abs(num(g) - num(c)) <= 1e-9 * abs(num(c)), (g.stdout[-200:], c.stdout[-200:])
+
+
+def test_reference_constant_speed_driver():
+    """test/constant-speed.c exits non-zero when the velocity drifts by more than 1e-10."""
+    r = run("dropin_constant-speed.test")
+    assert r.returncode == 0, r.stderr[-2000:]
+
+
+def test_reference_harmonic_driver_prints_the_golden_trajectory():
+    """test/harmonic.c prints r0 and E0 every step (:112-120); compare with harm.r0x/harm.E0x."""
+    r = run("dropin_harmonic.test")
+    assert r.returncode == 0, r.stderr[-2000:]
+    xs = [float(m.group(1)) for m in re.finditer(r"r0=\(([-+0-9.e]+) ", r.stderr)]
+    Es = [float(m.group(1)) for m in re.finditer(r"E0=\(([-+0-9.e]+) ", r.stderr)]
+    if not xs:
+        pytest.skip("the driver was built without GLOBAL_DEBUG (dbg output compiled out)")
+    r0 = np.loadtxt(os.path.join(GOLDEN, "harm.r0x"))
+    E0 = np.loadtxt(os.path.join(GOLDEN, "harm.E0x"))
+    n = min(len(xs), len(r0))
+    assert n >= 1000
+    assert np.abs(np.array(xs[:n]) - r0[:n]).max() < 1e-6
+    assert np.abs(np.array(Es[:n]) - E0[:n]).max() < 1e-8
+
+
+def test_reference_cli_and_output_layout(tmp_path):
+    """src/cpic.c main with output enabled: the reference's own output.c writes
+    <path>/bin/<iter>/{rho,phi,E_X,E_Y}.bin from the grids the GPU filled; the same run of the
+    CPU reference (cpic_ref, accumulate-correct deposit is not needed: position-delta config
+    without pack collisions) must give the same files to 1e-12."""
+    conf = (tmp_path / "out.conf")
+    text = open(os.path.join(ROOT, "conf", "two-streams.conf")).read()
+    text = text.replace("cycles = 800", "cycles = 6")
+
+    def with_output(path):
+        return text + f'\noutput = {{ path = "{path}" slices = 4 alignment = 512 }}\n'
+
+    outs = {}
+    for name, binary in (("gpu", "dropin_cpic"), ("cpu", "cpic_ref")):
+        d = tmp_path / name
+        conf.write_text(with_output(d))
+        r = run(binary, "-q", str(conf))
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs[name] = d
+    for it in range(6):
+        for f in ("rho", "phi", "E_X", "E_Y"):
+            a = np.fromfile(outs["gpu"] / "bin" / str(it) / f"{f}.bin")
+            b = np.fromfile(outs["cpu"] / "bin" / str(it) / f"{f}.bin")
+            assert a.shape == b.shape and a.size > 0
+            ok = np.isfinite(b)           # the reference leaves NaN in padding and unused rows
+            nx = 64
+            if f in ("rho", "phi"):       # padding columns nx, nx+1 hold FFT scratch: skip them
+                cols = (np.arange(a.size) % (nx + 2)) < nx
+                ok &= cols
+            scale = np.abs(b[ok]).max()
+            assert np.abs(a[ok] - b[ok]).max() <= 1e-12 * scale, (it, f)
+        assert (outs["gpu"] / "xdmf" / f"fields-iter{it}.xdmf").exists()
