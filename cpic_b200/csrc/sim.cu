@@ -818,12 +818,13 @@ launch_gather_push(sim_t_ *s, int is)
 	SpeciesHost &h = s->sp[is];
 	if(!h.block) return 0;
 	const Geom &g = s->g;
-	static bool attr_set[3] = { false, false, false };
+	/* the opt-in limit is per function and process wide: only ever raise it */
+	static size_t attr_smem[3] = { 0, 0, 0 };
 	const size_t smem = s->smem_push + (size_t) g.WPC * PIPE_STAGES * PipeArrays<MODE>::N * 32 * sizeof(double);
-	if(!attr_set[MODE] || smem > 48 * 1024)
+	if(smem > attr_smem[MODE])
 	{
 		CK(cudaFuncSetAttribute(k_gather_push<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-		attr_set[MODE] = true;
+		attr_smem[MODE] = smem;
 	}
 	const int ctas = s->nb / g.WPC;
 	/* a push reads the pending arrivals and fills the other outbox */
