@@ -41,6 +41,23 @@ def dbg(msg):
         print(f"[bench rank {os.environ.get('RANK', '0')}] {msg}", file=sys.stderr, flush=True)
 
 
+def ncu_traffic(kernel="k_gather_push<2>", path=None):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the
+    committed `ncu --set full` extract of the same workload (profiles/, config A, one GPU)."""
+    import csv
+    path = path or os.path.join(ROOT, "profiles", "r1e_ncu_full_summary.csv")
+    try:
+        rows = list(csv.reader(open(path)))
+        hdr = rows[0]
+        ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        vals = [float(r[ir]) + float(r[iw]) for r in rows[2:] if kernel in r[0]]
+        unit = rows[1][ir]
+        scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[unit]
+        return sum(vals) / len(vals) * scale if vals else None
+    except Exception:
+        return None
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -206,7 +223,9 @@ def main():
     conf = os.path.join(ROOT, "conf", name)
     params, run = load_conf(conf, rank=rank, nranks=world, device=local)
     params.nx, params.ny = nx, ny * world        # weak scaling: one nx x ny slab per GPU
-    params.Ly = params.Ly * world
+    # the cell size of the conf is kept (dx = 4/1024) whatever the grid: same cells-per-step physics
+    params.Lx = params.Lx * (nx / 1024)
+    params.Ly = params.Ly * (ny / 1024) * world
     # keep the physics of the conf: e0 scales with the particle density (plasma frequency fixed)
     params.e0 = params.e0 * (nps / 5_000_000) / ((nx / 1024) * (ny / 1024))
     nspecies = len(params.q)
@@ -262,6 +281,13 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
+    # ---- per-stage device time over another K steps (events around every stage; separate pass
+    # because the per-stage synchronisation perturbs the whole-step timing above)
+    sim.timing(True)
+    sim.run(args.steps)
+    stage_ms, launches = sim.get_timing()
+    dbg("stage timing done")
+    sim.timing(False)
     # the same count on every rank (the steps contain collectives)
     reps = int(min(60, max(0, (1500.0 - (time.perf_counter() - t_clk) * 1e3) / max(ms, 1e-3))))
     r_t = torch.tensor([reps], dtype=torch.int64, device="cuda")
@@ -277,13 +303,6 @@ def main():
         clk["window"] = "warm-up + timed region + repeats of the same steps (%.1f s)" % (time.perf_counter() - t_clk)
     value = n_total * args.steps / (ms * 1e-3)
 
-    # ---- per-stage device time over another K steps (events around every stage; separate pass
-    # because the per-stage synchronisation perturbs the whole-step timing above)
-    sim.timing(True)
-    sim.run(args.steps)
-    stage_ms, launches = sim.get_timing()
-    dbg("stage timing done")
-    sim.timing(False)
     peak, peak_src = measured_peak()
     k_launches = args.steps * nspecies
     t_push = stage_ms["gather_push"] / k_launches          # ms per k_gather_push launch
@@ -291,7 +310,9 @@ def main():
     t_dep = stage_ms["field_rho"] / args.steps
     roofline = {"bound": "hbm", "kernel": "k_gather_push<2> (fused field gather + Boris push)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "peak_source": peak_src, "traffic": None,
+                "peak_source": peak_src,
+                "traffic": ncu_traffic() if (world == 1 and args.workload == "A") else None,
+                "traffic_source": "profiles/r1e_ncu_full_summary.csv (bytes per launch, mean of the two species)",
                 "algorithmic_bytes_per_particle": BYTES_GATHER_PUSH, "particles_per_launch": nps,
                 "avg_launch_ms": t_push,
                 "whole_step_frac": (n_rank * args.steps / (ms * 1e-3)) * (BYTES_GATHER_PUSH + BYTES_DEPOSIT) / 1e9 / peak,
@@ -326,10 +347,12 @@ def main():
             dist.all_reduce(te_t, op=dist.ReduceOp.MAX)
         te = float(te_t.item())
         L.cpic_b200_host_free(host)
-        e2e = {"value": n_total * e_steps / te, "unit": UNIT, "h2d_bytes_per_step": int(nbytes),
-               "d2h_bytes_per_step": int(nbytes + fbytes), "steps": e_steps,
-               "note": "particle state round-trips through pinned host memory every step (worst case of the "
-                       "drop-in: host-owned plist); resident mode only reads the grids back"}
+        moved = n_rank * 48 + 8 * nspecies + 4 * nspecies * ((params.nx // 8) * (params.ny // world // 8))
+        e2e = {"value": n_total * e_steps / te, "unit": UNIT, "h2d_bytes_per_step": int(moved),
+               "d2h_bytes_per_step": int(moved + fbytes), "steps": e_steps,
+               "note": "the whole particle state (x,y,ux,uy,uz,id of every particle) is uploaded from pinned host "
+                       "memory before and downloaded after every sim_step, plus the four grids: the worst case of "
+                       "the drop-in (host-owned particle lists); a resident run only reads the grids back"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

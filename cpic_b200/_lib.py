@@ -33,7 +33,7 @@ class ParamsC(C.Structure):
                 ("q", C.c_double * MAX_SPECIES), ("m", C.c_double * MAX_SPECIES),
                 ("rank", C.c_int32), ("nranks", C.c_int32), ("device", C.c_int32),
                 ("capacity_factor", C.c_double), ("keep_particle_E", C.c_int32),
-                ("outbox_fraction", C.c_double)]
+                ("block_cells", C.c_int32), ("outbox_fraction", C.c_double)]
 
 
 class RunC(C.Structure):

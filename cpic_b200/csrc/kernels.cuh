@@ -129,6 +129,15 @@ tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar)
 			: "memory");
 }
 
+/* 1D bulk copy global->shared through the TMA unit (UBLKCP): `bytes` multiple of 16, both
+ * addresses 16 B aligned; completes on the mbarrier */
+__device__ __forceinline__ void
+tma_bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+			:: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 /* 8-byte asynchronous global->shared copy (LDGSTS): the particle pipeline's prefetch */
 __device__ __forceinline__ void
 cp_async8(void *dst, const void *src)
@@ -381,6 +390,7 @@ arrival_slot(const Arrivals &A, const SpeciesDev &sp, int f)
  * Ranks inside a batch come from ballots, so the order is: batches in order, lanes in
  * order. MODE 0 moves nothing. */
 #define PIPE_STAGES 3
+#define PUSH_SMEM_HEADER 384      /* tile barrier + MAX_WPC * PIPE_STAGES stage barriers */
 
 /* arrays staged per batch: x y (ux uy uz id) (Ex Ey) */
 template <int MODE> struct PipeArrays { static const int N = MODE == 0 ? 2 : MODE == 2 ? 6 : 8; };
@@ -393,9 +403,10 @@ k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 {
 	constexpr int NARR = PipeArrays<MODE>::N;
 	extern __shared__ __align__(128) unsigned char smem[];
-	uint64_t *bar = (uint64_t *) smem;
-	int *wscratch = (int *) (smem + 128) + (threadIdx.x >> 5) * 32;   /* 32 ints per warp */
-	double *tEx = (double *) (smem + 128 + MAX_WPC * 32 * sizeof(int));
+	uint64_t *bar = (uint64_t *) smem;                                  /* E tile barrier */
+	uint64_t *sbar = (uint64_t *) (smem + 16) + (threadIdx.x >> 5) * PIPE_STAGES;   /* per warp, per stage */
+	int *wscratch = (int *) (smem + PUSH_SMEM_HEADER) + (threadIdx.x >> 5) * 32;   /* 32 ints per warp */
+	double *tEx = (double *) (smem + PUSH_SMEM_HEADER + MAX_WPC * 32 * sizeof(int));
 	double *tEy = tEx + g.tile_dbl;
 	/* per-warp ring of PIPE_STAGES batches x NARR arrays x 32 lanes */
 	double *ring = tEy + g.tile_dbl + (threadIdx.x >> 5) * (PIPE_STAGES * NARR * 32);
@@ -408,6 +419,8 @@ k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 	const int b = by * g.nbx + bx;
 	int *ocnt = wscratch + 18;       /* leavers per destination code so far */
 	if(lane < 9) ocnt[lane] = 0;
+	if(lane < PIPE_STAGES) mbar_init(sbar + lane, 1);
+	__syncwarp();
 
 	if(MODE != 1 && threadIdx.x == 0)
 	{
@@ -422,50 +435,71 @@ k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 	 * previous push's outbox and fills `cur` */
 	const Outbox &in = sp.ob[MODE == 0 ? cur : cur ^ 1];
 	const Outbox &out = sp.ob[cur];
-	const Arrivals A = find_arrivals(in, sp.nob, g, nb, b, lane, wscratch);
 	const int cnt = sp.count[b];
 	const unsigned base = (unsigned) b * (unsigned) sp.cap;      /* slot indices fit 32 bits (checked on the host) */
 	const int tx0 = cx * g.WPC * g.BX, ty0 = by * g.BY;   /* tile origin in cells */
 	const int gby = g.brow0 + by;
 	/* the walk: nbo batches over the own segment, then nba over the arrivals */
-	const int nbo = (cnt + 31) >> 5, nba = (A.total + 31) >> 5, nbt = nbo + nba;
+	const int nbo = (cnt + 31) >> 5;
+	Arrivals A;                      /* filled below, once the first loads are in flight */
+	A.total = 0; A.start = wscratch; A.src = wscratch + 9;
 	int w = 0;                       /* write cursor of the segment */
 	int bad = 0;
 	unsigned idmask = 0;             /* bit (bi % PIPE_STAGES): the ids of that staged batch were fetched */
 
 	/* Stage batch bi: every lane copies its own element of every array into the ring
-	 * (asynchronously, no registers held); with_id also fetches the ids. Returns the
-	 * lane's source slot through the ring itself (array slot NARR-1 reused as index for
-	 * MODE 0 is not needed: the slot is recomputed). */
+	 * (asynchronously, no registers held); with_id also fetches the ids. */
 #define ISSUE_BATCH(bi, with_id) do { \
 	const bool own_ = (bi) < nbo; \
-	const int t_ = (own_ ? (bi) : (bi) - nbo) * 32 + lane; \
-	double *st_ = ring + ((bi) % PIPE_STAGES) * (NARR * 32) + lane; \
+	double *st0_ = ring + ((bi) % PIPE_STAGES) * (NARR * 32); \
 	if(with_id) idmask |= 1u << ((bi) % PIPE_STAGES); else idmask &= ~(1u << ((bi) % PIPE_STAGES)); \
-	if(t_ < (own_ ? cnt : A.total)) { \
-		if(own_) { \
-			const unsigned q_ = base + t_; \
-			cp_async8(st_ + 0 * 32, sp.x + q_); cp_async8(st_ + 1 * 32, sp.y + q_); \
-			if(MODE != 0) { cp_async8(st_ + 2 * 32, sp.ux + q_); cp_async8(st_ + 3 * 32, sp.uy + q_); \
-				cp_async8(st_ + 4 * 32, sp.uz + q_); if(with_id) cp_async8(st_ + 5 * 32, sp.id + q_); } \
-			if(MODE == 1) { cp_async8(st_ + 6 * 32, sp.pEx + q_); cp_async8(st_ + 7 * 32, sp.pEy + q_); } \
-		} else { \
+	if(own_) { \
+		/* a whole batch of the segment is 256 contiguous, aligned bytes per array: one TMA \
+		 * bulk copy each, issued by one lane, landing on the stage's mbarrier */ \
+		if(lane == 0) { \
+			const unsigned q_ = base + (bi) * 32; \
+			uint64_t *mb_ = sbar + (bi) % PIPE_STAGES; \
+			const int na_ = (MODE == 0 ? 2 : 5) + ((MODE != 0 && (with_id)) ? 1 : 0) + (MODE == 1 ? 2 : 0); \
+			mbar_expect_tx(mb_, (uint32_t) na_ * 256u); \
+			tma_bulk_load(st0_ + 0 * 32, sp.x + q_, 256, mb_); tma_bulk_load(st0_ + 1 * 32, sp.y + q_, 256, mb_); \
+			if(MODE != 0) { tma_bulk_load(st0_ + 2 * 32, sp.ux + q_, 256, mb_); tma_bulk_load(st0_ + 3 * 32, sp.uy + q_, 256, mb_); \
+				tma_bulk_load(st0_ + 4 * 32, sp.uz + q_, 256, mb_); if(with_id) tma_bulk_load(st0_ + 5 * 32, sp.id + q_, 256, mb_); } \
+			if(MODE == 1) { tma_bulk_load(st0_ + 6 * 32, sp.pEx + q_, 256, mb_); tma_bulk_load(st0_ + 7 * 32, sp.pEy + q_, 256, mb_); } \
+		} \
+	} else { \
+		/* arrivals are scattered over up to eight runs: per-lane 8-byte async copies */ \
+		const int t_ = ((bi) - nbo) * 32 + lane; \
+		double *st_ = st0_ + lane; \
+		if(t_ < A.total) { \
 			const unsigned q_ = (unsigned) arrival_slot(A, sp, t_); \
 			cp_async8(st_ + 0 * 32, in.x + q_); cp_async8(st_ + 1 * 32, in.y + q_); \
 			if(MODE != 0) { cp_async8(st_ + 2 * 32, in.ux + q_); cp_async8(st_ + 3 * 32, in.uy + q_); \
 				cp_async8(st_ + 4 * 32, in.uz + q_); if(with_id) cp_async8(st_ + 5 * 32, in.id + q_); } \
 			if(MODE == 1) { cp_async8(st_ + 6 * 32, in.Ex + q_); cp_async8(st_ + 7 * 32, in.Ey + q_); } \
 		} \
-	} \
-	cp_async_commit(); } while(0)
+		cp_async_commit(); \
+	} } while(0)
 
-	/* prologue: PIPE_STAGES-1 batches in flight while the tile lands */
+	/* Prologue: the first batches of the own segment go out before anything else is known;
+	 * the neighbours' counters (the arrivals) are fetched while those loads and the tile are
+	 * in flight. Ids are only needed by particles that change slot: every arrival, and
+	 * segment particles once a leaver has opened a gap. A block that receives particles
+	 * almost surely loses some as well, so such a block fetches its ids from the first batch
+	 * on; a quiet block fetches them from the point where the write cursor lags (one late
+	 * fetch covers the batches already in flight). */
 #pragma unroll
 	for(int k = 0; k < PIPE_STAGES - 1; k++)
-	{
-		if(k < nbt) ISSUE_BATCH(k, k >= nbo);
-		else cp_async_commit();
-	}
+		if(k < nbo) ISSUE_BATCH(k, true);
+	A = find_arrivals(in, sp.nob, g, nb, b, lane, wscratch);
+	const bool busy = A.total > 0;
+	const int nba = (A.total + 31) >> 5, nbt = nbo + nba;
+#pragma unroll
+	for(int k = 0; k < PIPE_STAGES - 1; k++)
+		if(k >= nbo)
+		{
+			if(k < nbt) ISSUE_BATCH(k, true);
+			else cp_async_commit();
+		}
 
 	if(MODE != 1)
 	{
@@ -489,10 +523,17 @@ k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 		 * cursor lags the read position (a late fetch covers the batch where that starts). */
 		{
 			const int bn = bi + PIPE_STAGES - 1;
-			if(bn < nbt) ISSUE_BATCH(bn, bn >= nbo || w != bi * 32);
+			if(bn < nbt) ISSUE_BATCH(bn, busy || bn >= nbo || w != bi * 32);
 			else cp_async_commit();
 		}
-		cp_async_wait<PIPE_STAGES - 1>();                /* batch bi has landed (own copies) */
+		/* batch bi has landed: segment batches on their stage barrier (its parity flips every
+		 * reuse), arrival batches when their own async-copy group is the oldest but
+		 * PIPE_STAGES-1 (every batch index >= nbo, real or not, commits exactly one group) */
+		if(own)
+		{
+			if(mbar_wait(sbar + bi % PIPE_STAGES, (bi / PIPE_STAGES) & 1)) { atomicOr(errflag, ERRBIT_TMA); break; }
+		}
+		else cp_async_wait<PIPE_STAGES - 1>();
 
 		const double *st = ring + (bi % PIPE_STAGES) * (NARR * 32) + lane;
 		const bool have_id = (idmask >> (bi % PIPE_STAGES)) & 1;
@@ -902,6 +943,31 @@ k_deposit(SpeciesDev sp, Geom g, double vq, int nb, int arr,
 		if(FIRST) *dst = v;
 		else *dst += v;
 	}
+}
+
+/* Compact image of a species for host round trips: the live particles of every block, block
+ * after block, without the slack of the segments. pack != 0: segments -> image, else
+ * image -> segments. The image holds n values per array (x y ux uy uz id), `off` the
+ * exclusive prefix of the block counts. One warp per block. */
+static __global__ void __launch_bounds__(256)
+k_image_copy(SpeciesDev sp, int nb, const int *__restrict__ cnt, const long long *__restrict__ off,
+		double *__restrict__ img, long long n, int pack)
+{
+	const int lane = threadIdx.x & 31;
+	const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	if(b >= nb) return;
+	const int c = cnt[b];
+	const long long o = off[b];
+	const size_t base = (size_t) b * sp.cap;
+	double *arr[6] = { sp.x, sp.y, sp.ux, sp.uy, sp.uz, (double *) sp.id };
+#pragma unroll
+	for(int a = 0; a < 6; a++)
+		for(int i = lane; i < c; i += 32)
+		{
+			if(pack) img[(size_t) a * n + o + i] = arr[a][base + i];
+			else arr[a][base + i] = img[(size_t) a * n + o + i];
+		}
+	if(!pack && lane == 0) sp.count[b] = c;
 }
 
 /* Kinetic energy per species: sum(ux^2 + uy^2), reference src/sim.c:366-395 (compiled

@@ -76,6 +76,9 @@ struct cpic_b200_sim {
 	bool have_plans;
 	double *hb, *hr, *hc;    /* deposit halos */
 	double *red;             /* reduction scratch */
+	double *img;             /* staging of the compact particle image */
+	long long *img_off;
+	size_t img_cap;
 	int *errflag;
 	int *h_err;              /* pinned */
 	CUtensorMap mapEx, mapEy;
@@ -182,15 +185,22 @@ cpic_b200_create(const cpic_b200_params_t *pp, cpic_b200_sim_t **out)
 	g.ny = (int) (p.ny / p.nranks);
 	g.row0 = p.rank * g.ny;
 	g.S = 2 * (g.nx / 2 + 1);
-	g.BX = pick_div(g.nx, 8);
-	g.BY = pick_div(g.ny, 8);
-	g.lBX = g.BX == 8 ? 3 : g.BX == 4 ? 2 : g.BX == 2 ? 1 : 0;
-	g.lBY = g.BY == 8 ? 3 : g.BY == 4 ? 2 : g.BY == 2 ? 1 : 0;
+	int bc = p.block_cells > 0 ? p.block_cells : 8;
+	if(getenv("CPIC_B200_BLOCK_CELLS")) bc = atoi(getenv("CPIC_B200_BLOCK_CELLS"));
+	if(bc != 1 && bc != 2 && bc != 4 && bc != 8 && bc != 16 && bc != 32)
+	{
+		delete s;
+		return fail(CPIC_B200_EINVAL, "block_cells must be a power of two between 1 and 32");
+	}
+	g.BX = pick_div(g.nx, bc);
+	g.BY = pick_div(g.ny, bc);
+	g.lBX = 0; while((1 << g.lBX) < g.BX) g.lBX++;
+	g.lBY = 0; while((1 << g.lBY) < g.BY) g.lBY++;
 	g.nbx = g.nx / g.BX;
 	g.nby = g.ny / g.BY;
 	g.nby_glob = g.nby * p.nranks;
 	g.brow0 = p.rank * g.nby;
-	g.WPC = pick_div(g.nbx, MAX_WPC);
+	g.WPC = pick_div(g.nbx, g.BX > 8 ? MAX_WPC / 2 : MAX_WPC);
 	g.TW = g.WPC * g.BX + 2;
 	if(g.TW & 1) g.TW++;
 	g.TH = g.BY + 1;
@@ -274,7 +284,7 @@ cpic_b200_create(const cpic_b200_params_t *pp, cpic_b200_sim_t **out)
 
 	/* barrier + per-warp scratch + two E tiles + per-warp prefetch rings (sized for the
 	 * widest mode: 8 arrays) */
-	s->smem_push = 128 + MAX_WPC * 32 * sizeof(int) + 2 * tile_bytes(g);
+	s->smem_push = PUSH_SMEM_HEADER + MAX_WPC * 32 * sizeof(int) + 2 * tile_bytes(g);
 	s->smem_dep = (size_t) g.WPC * (g.BX + 1) * (g.BY + 1) * sizeof(double);
 
 	for(int i = 0; i < p.nspecies; i++) { s->sp[i].q = p.q[i]; s->sp[i].m = p.m[i]; }
@@ -307,7 +317,7 @@ cpic_b200_destroy(cpic_b200_sim_t *s)
 	if(s->have_plans) { cufftDestroy(s->plan_fwd); cufftDestroy(s->plan_inv); }
 	cudaFree(s->rho); cudaFree(s->phi); cudaFree(s->phi_raw); cudaFree(s->Ex); cudaFree(s->Ey);
 	cudaFree(s->G); cudaFree(s->gk); cudaFree(s->hb); cudaFree(s->hr); cudaFree(s->hc);
-	cudaFree(s->red); cudaFree(s->errflag);
+	cudaFree(s->red); cudaFree(s->errflag); cudaFree(s->img); cudaFree(s->img_off);
 	if(s->h_err) cudaFreeHost(s->h_err);
 	if(s->ev[0]) cudaEventDestroy(s->ev[0]);
 	if(s->ev[1]) cudaEventDestroy(s->ev[1]);
@@ -1150,47 +1160,110 @@ cpic_b200_energy(cpic_b200_sim_t *s, double *kinetic, double *potential)
 
 /* -------------------------------------------------- raw images (bench e2e) */
 
+/* Image layout (host): per species { int64 n; int32 count[nb] (padded to 8 bytes);
+ * double x[n], y[n], ux[n], uy[n], uz[n]; int64 id[n] }. Sized for the particle numbers
+ * at the time of the call plus 12.5 % (the population of a rank changes with several ranks). */
+static int64_t
+image_species_bytes(const sim_t_ *s, int64_t n)
+{
+	return 8 + (((int64_t) s->nb * 4 + 7) & ~7LL) + 6 * 8 * n;
+}
+
 extern "C" int64_t
 cpic_b200_image_bytes(cpic_b200_sim_t *s)
 {
 	if(!s) return -1;
-	int64_t n = 0;
-	for(int is = 0; is < s->p.nspecies; is++) n += (int64_t) s->sp[is].block_bytes;
-	return n;
+	int64_t bytes = 0;
+	for(int is = 0; is < s->p.nspecies; is++)
+	{
+		if(!s->sp[is].block) continue;
+		int64_t n = cpic_b200_num_particles(s, is);
+		if(n < 0) return -1;
+		bytes += image_species_bytes(s, n + n / 8 + 1024);
+	}
+	return bytes;
+}
+
+static int
+image_staging(sim_t_ *s, size_t doubles)
+{
+	if(doubles <= s->img_cap) return 0;
+	cudaFree(s->img);
+	cudaFree(s->img_off);
+	s->img = NULL; s->img_off = NULL; s->img_cap = 0;
+	CK(cudaMalloc(&s->img, doubles * sizeof(double)));
+	CK(cudaMalloc(&s->img_off, ((size_t) s->nb + 1) * (sizeof(long long) + sizeof(int))));
+	s->img_cap = doubles;
+	return 0;
 }
 
 extern "C" int
 cpic_b200_image_download(cpic_b200_sim_t *s, void *host, int64_t bytes)
 {
-	if(!s || !host || bytes < cpic_b200_image_bytes(s)) return fail(CPIC_B200_EINVAL, "image buffer too small");
+	if(!s || !host) return fail(CPIC_B200_EINVAL, "null argument");
 	CK(cudaSetDevice(s->device));
-	char *p = (char *) host;
+	char *p = (char *) host, *end = p + bytes;
+	std::vector<int> cnt((size_t) s->nb);
+	std::vector<long long> off((size_t) s->nb);
 	for(int is = 0; is < s->p.nspecies; is++)
 	{
 		SpeciesHost &h = s->sp[is];
 		if(!h.block) continue;
-		if(absorb(s, is)) return CPIC_B200_ECUDA;
-		CK(cudaMemcpyAsync(p, h.block, h.block_bytes, cudaMemcpyDeviceToHost, s->stream));
-		p += h.block_bytes;
+		int rc = absorb(s, is);
+		if(rc) return rc;
+		CK(cudaMemcpyAsync(cnt.data(), h.d.count, cnt.size() * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+		CK(cudaStreamSynchronize(s->stream));
+		long long n = 0;
+		for(int b = 0; b < s->nb; b++) { off[(size_t) b] = n; n += cnt[(size_t) b]; }
+		if(p + image_species_bytes(s, n) > end) return fail(CPIC_B200_EINVAL, "image buffer too small");
+		if((rc = image_staging(s, (size_t) 6 * n))) return rc;
+		CK(cudaMemcpyAsync(s->img_off, off.data(), off.size() * sizeof(long long), cudaMemcpyHostToDevice, s->stream));
+		k_image_copy<<<(s->nb + 7) / 8, 256, 0, s->stream>>>(h.d, s->nb, h.d.count, s->img_off, s->img, n, 1);
+		CK(cudaGetLastError());
+		*(int64_t *) p = n; p += 8;
+		memcpy(p, cnt.data(), cnt.size() * sizeof(int)); p += ((int64_t) s->nb * 4 + 7) & ~7LL;
+		CK(cudaMemcpyAsync(p, s->img, (size_t) 6 * n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+		p += 6 * 8 * n;
+		CK(cudaStreamSynchronize(s->stream));
 	}
-	CK(cudaStreamSynchronize(s->stream));
 	return 0;
 }
 
 extern "C" int
 cpic_b200_image_upload(cpic_b200_sim_t *s, const void *host, int64_t bytes)
 {
-	if(!s || !host || bytes < cpic_b200_image_bytes(s)) return fail(CPIC_B200_EINVAL, "image buffer too small");
+	if(!s || !host) return fail(CPIC_B200_EINVAL, "null argument");
 	CK(cudaSetDevice(s->device));
-	const char *p = (const char *) host;
+	const char *p = (const char *) host, *end = p + bytes;
+	std::vector<long long> off((size_t) s->nb);
 	for(int is = 0; is < s->p.nspecies; is++)
 	{
 		SpeciesHost &h = s->sp[is];
 		if(!h.block) continue;
-		/* the image holds every particle in the segments: no arrivals are pending */
+		if(p + 8 > end) return fail(CPIC_B200_EINVAL, "truncated image");
+		const long long n = *(const int64_t *) p; p += 8;
+		const int *cnt = (const int *) p; p += ((int64_t) s->nb * 4 + 7) & ~7LL;
+		if(n < 0 || p + 6 * 8 * n > end) return fail(CPIC_B200_EINVAL, "truncated image");
+		long long m = 0;
+		for(int b = 0; b < s->nb; b++)
+		{
+			if(cnt[b] < 0 || cnt[b] > h.d.cap) return fail(CPIC_B200_ECAPACITY, "image block %d holds %d particles, capacity %d", b, cnt[b], h.d.cap);
+			off[(size_t) b] = m; m += cnt[b];
+		}
+		if(m != n) return fail(CPIC_B200_EINVAL, "image counts do not add up");
+		int rc = image_staging(s, (size_t) 6 * n);
+		if(rc) return rc;
+		int *dcnt = (int *) (s->img_off + s->nb + 1);
+		/* the image holds every particle: no arrivals are pending afterwards */
 		for(int k = 0; k < 2; k++) CK(cudaMemsetAsync(h.d.ob[k].count, 0, (size_t) s->nob * 9 * sizeof(int), s->stream));
-		CK(cudaMemcpyAsync(h.block, p, h.block_bytes, cudaMemcpyHostToDevice, s->stream));
-		p += h.block_bytes;
+		CK(cudaMemcpyAsync(s->img_off, off.data(), off.size() * sizeof(long long), cudaMemcpyHostToDevice, s->stream));
+		CK(cudaMemcpyAsync(dcnt, cnt, (size_t) s->nb * sizeof(int), cudaMemcpyHostToDevice, s->stream));
+		CK(cudaMemcpyAsync(s->img, p, (size_t) 6 * n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+		k_image_copy<<<(s->nb + 7) / 8, 256, 0, s->stream>>>(h.d, s->nb, dcnt, s->img_off, s->img, n, 0);
+		CK(cudaGetLastError());
+		/* `off` is reused by the next species: the copies above must have left the host */
+		CK(cudaStreamSynchronize(s->stream));
+		p += 6 * 8 * n;
 	}
 	return 0;
 }

@@ -30,6 +30,7 @@ class Params:
     capacity_factor: float = 0.0
     keep_particle_E: bool = False
     outbox_fraction: float = 0.0
+    block_cells: int = 0
 
     def to_c(self):
         p = ParamsC()
@@ -44,6 +45,7 @@ class Params:
         p.capacity_factor = self.capacity_factor
         p.keep_particle_E = int(self.keep_particle_E)
         p.outbox_fraction = self.outbox_fraction
+        p.block_cells = self.block_cells
         return p
 
     @staticmethod
@@ -51,7 +53,7 @@ class Params:
         n = p.nspecies
         return Params(p.nx, p.ny, p.Lx, p.Ly, p.dt, p.e0, tuple(p.B), tuple(p.q[:n]), tuple(p.m[:n]),
                       p.plasma_chunks, p.rank, p.nranks, p.device, p.capacity_factor, bool(p.keep_particle_E),
-                      p.outbox_fraction)
+                      p.outbox_fraction, p.block_cells)
 
 
 @dataclass

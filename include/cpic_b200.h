@@ -59,6 +59,7 @@ typedef struct cpic_b200_params {
 	int32_t device;             /* CUDA device ordinal, -1 = current */
 	double capacity_factor;     /* particle-block slack over the fullest block, 0 = default (1.5) */
 	int32_t keep_particle_E;    /* 1: stage_plasma_r also keeps the gathered E per particle */
+	int32_t block_cells;        /* cells per particle-block side (power of two <= 32), 0 = default (8) */
 	double outbox_fraction;     /* exchange buffer per block side as a share of the block capacity,
 	                             * 0 = default (0.5); corners get a quarter of it */
 } cpic_b200_params_t;
@@ -149,8 +150,10 @@ int cpic_b200_energy(cpic_b200_sim_t *sim, double *kinetic, double *potential);
 int cpic_b200_timing(cpic_b200_sim_t *sim, int enable);
 int cpic_b200_get_timing(cpic_b200_sim_t *sim, double ms[5], int64_t launches[1]);
 
-/* Raw particle-block image for host<->device round trips (bench e2e): the caller owns a
- * pinned buffer of cpic_b200_image_bytes(); download fills it, upload restores it. */
+/* Compact particle image for host<->device round trips (bench e2e, checkpoints): the live
+ * particles of every block, block after block, with the block counts. The caller owns a
+ * (pinned) buffer of cpic_b200_image_bytes(); download fills it, upload restores the exact
+ * device state (order included). */
 int64_t cpic_b200_image_bytes(cpic_b200_sim_t *sim);
 int cpic_b200_image_download(cpic_b200_sim_t *sim, void *host, int64_t bytes);
 int cpic_b200_image_upload(cpic_b200_sim_t *sim, const void *host, int64_t bytes);

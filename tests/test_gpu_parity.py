@@ -205,3 +205,32 @@ def test_far_movers():
         assert g.num_particles(0) == n
         assert_close(field_errors(g, o), what=f"far movers fields, iteration {it}")
         assert_close(particle_errors(g, o, p), what=f"far movers particles, iteration {it}")
+
+
+def test_image_round_trip_is_exact():
+    """cpic_b200_image_download / _upload (the e2e path of bench.py): the device state after an
+    upload continues bit-identically."""
+    import ctypes as C
+    a, _, params, _ = pair_from_conf(conf_path("2d-2species-small.conf"))
+    b, _, _, _ = pair_from_conf(conf_path("2d-2species-small.conf"))
+    for _ in range(4):
+        a.step()
+        b.step()
+    L = b.L
+    n = L.cpic_b200_image_bytes(b.h)
+    host = L.cpic_b200_host_alloc(n)
+    assert host
+    for _ in range(5):
+        assert L.cpic_b200_image_download(b.h, host, n) == 0
+        assert L.cpic_b200_image_upload(b.h, host, n) == 0
+        a.step()
+        b.step()
+    a.sync()
+    b.sync()
+    L.cpic_b200_host_free(host)
+    for name in ("rho", "phi", "Ex", "Ey"):
+        assert relerr(b.raw_field(name), a.raw_field(name)) <= TOL
+    for i in range(len(params.q)):
+        pa, pb = a.particles(i), b.particles(i)
+        for k in ("id", "x", "y", "ux", "uy"):
+            assert np.array_equal(pa[k], pb[k]), (i, k)
