@@ -4,8 +4,8 @@
  *   rho ghost row      src/comm_field.c:51-136   ncclSend/Recv of nx doubles on the rank ring
  *   phi ghost rows     src/comm_field.c:139-201  2 rows north, 1 row south, padding included
  *   particles (Y pass) src/comm_plasma.c:887-1120  the outbox regions of the edge block rows
- *                      that point across the slab face, straight into the neighbour's ghost
- *                      outbox rows (no packing: regions are stored code-major)
+ *                      that point across the slab face, gathered into one message per face
+ *                      for all species, into the neighbour's ghost outbox rows
  *   FFT transposes     FFTW-MPI inside src/solver.c:485,491: row FFTs, all-to-all, column
  *                      FFTs with the Green's function applied in the transposed layout,
  *                      all-to-all back, row FFTs (2 exchanges per solve; FFTW does 4)
@@ -304,21 +304,30 @@ face_layout(const SpeciesDev *sp, int nbx, int code0)
 	return L;
 }
 
-/* The Y pass of comm_plasma between ranks (reference src/comm_plasma.c:1039-1120).
- * Row 0's regions with codes 0,1,2 (moving north) land in the north rank's south ghost
- * row; the last row's regions with codes 6,7,8 in the south rank's north ghost row.
- * One message per face: a small kernel gathers the regions and their counts into a
- * contiguous buffer, NCCL moves it, another kernel scatters it into the ghost rows. */
+/* The Y pass of comm_plasma between ranks (reference src/comm_plasma.c:1039-1120), all
+ * species at once. Row 0's regions with codes 0,1,2 (moving north) land in the north rank's
+ * south ghost row; the last row's regions with codes 6,7,8 in the south rank's north ghost
+ * row. One message per face: small kernels gather every species' regions and counts into a
+ * contiguous buffer, one NCCL group moves both faces, and the mirror kernels scatter them
+ * into the ghost rows. */
 int
-comm_particles(Comm *c, SpeciesDev *sp, int arr, const Geom &g, int nb, cudaStream_t stream,
-		int *errflag, long long *launches)
+comm_particles(Comm *c, SpeciesDev *const *sps, const int *arrs, int nsp, const Geom &g, int nb,
+		cudaStream_t stream, int *errflag, long long *launches)
 {
 	(void) errflag;
 	const int south = (c->rank + 1) % c->n, north = (c->rank + c->n - 1) % c->n;
 	const int nbx = g.nbx;
-	const FaceLayout Ln = face_layout(sp, nbx, 0), Ls = face_layout(sp, nbx, 6);
-	/* both layouts have the same size (corner, side, corner) */
-	const size_t doubles = (size_t) Ln.total + (3 * (size_t) nbx + 1) / 2;
+	FaceLayout Ln[8], Ls[8];
+	size_t off[9];
+	off[0] = 0;
+	for(int i = 0; i < nsp; i++)
+	{
+		Ln[i] = face_layout(sps[i], nbx, 0);
+		Ls[i] = face_layout(sps[i], nbx, 6);
+		/* both layouts have the same size (corner, side, corner) */
+		off[i + 1] = off[i] + (size_t) Ln[i].total + (3 * (size_t) nbx + 1) / 2;
+	}
+	const size_t doubles = off[nsp];
 	if(doubles > c->face_cap)
 	{
 		for(int k = 0; k < 4; k++) cudaFree(c->face[k]);
@@ -326,10 +335,13 @@ comm_particles(Comm *c, SpeciesDev *sp, int arr, const Geom &g, int nb, cudaStre
 		for(int k = 0; k < 4; k++) CCK(cudaMalloc(&c->face[k], c->face_cap * sizeof(double)));
 	}
 	double *send_n = c->face[0], *send_s = c->face[1], *recv_s = c->face[2], *recv_n = c->face[3];
-	const unsigned threads = Ln.total + 3u * nbx;
-	const int blocks = (int) ((threads + 255) / 256);
-	k_face_copy<<<blocks, 256, 0, stream>>>(*sp, arr, nbx, 0, 0, Ln, send_n, 1);
-	k_face_copy<<<blocks, 256, 0, stream>>>(*sp, arr, nbx, nb - nbx, 6, Ls, send_s, 1);
+	for(int i = 0; i < nsp; i++)
+	{
+		const unsigned threads = Ln[i].total + 3u * nbx;
+		const int blocks = (int) ((threads + 255) / 256);
+		k_face_copy<<<blocks, 256, 0, stream>>>(*sps[i], arrs[i], nbx, 0, 0, Ln[i], send_n + off[i], 1);
+		k_face_copy<<<blocks, 256, 0, stream>>>(*sps[i], arrs[i], nbx, nb - nbx, 6, Ls[i], send_s + off[i], 1);
+	}
 	NCK(g_nccl.GroupStart());
 	NCK(g_nccl.Send(send_n, doubles, ncclFloat64, north, c->nc, stream));
 	NCK(g_nccl.Send(send_s, doubles, ncclFloat64, south, c->nc, stream));
@@ -337,10 +349,15 @@ comm_particles(Comm *c, SpeciesDev *sp, int arr, const Geom &g, int nb, cudaStre
 	NCK(g_nccl.Recv(recv_n, doubles, ncclFloat64, north, c->nc, stream));
 	NCK(g_nccl.GroupEnd());
 	/* what the south rank sent north (codes 0,1,2) fills our south ghost row, and vice versa */
-	k_face_copy<<<blocks, 256, 0, stream>>>(*sp, arr, nbx, nb + nbx, 0, Ln, recv_s, 0);
-	k_face_copy<<<blocks, 256, 0, stream>>>(*sp, arr, nbx, nb, 6, Ls, recv_n, 0);
+	for(int i = 0; i < nsp; i++)
+	{
+		const unsigned threads = Ln[i].total + 3u * nbx;
+		const int blocks = (int) ((threads + 255) / 256);
+		k_face_copy<<<blocks, 256, 0, stream>>>(*sps[i], arrs[i], nbx, nb + nbx, 0, Ln[i], recv_s + off[i], 0);
+		k_face_copy<<<blocks, 256, 0, stream>>>(*sps[i], arrs[i], nbx, nb, 6, Ls[i], recv_n + off[i], 0);
+	}
 	CCK(cudaGetLastError());
-	if(launches) *launches += 4;
+	if(launches) *launches += 4 * nsp;
 	return 0;
 }
 

@@ -24,8 +24,8 @@ int comm_rho_halo(Comm *c, double *rho, cudaStream_t stream, long long *launches
 int comm_phi_halo(Comm *c, double *phi, cudaStream_t stream);
 /* particles: outbox entries of the edge block rows that leave the slab are sent to the
  * neighbour ranks and land in the ghost outbox rows nb .. nb+2*nbx */
-int comm_particles(Comm *c, SpeciesDev *sp, int arr, const Geom &g, int nb, cudaStream_t stream,
-		int *errflag, long long *launches);
+int comm_particles(Comm *c, SpeciesDev *const *sps, const int *arrs, int nsp, const Geom &g, int nb,
+		cudaStream_t stream, int *errflag, long long *launches);
 /* distributed MFT solve: rho slab rows -> unnormalised phi slab rows (ny x S) */
 int comm_solve(Comm *c, const double *rho, double *phi_raw, cudaStream_t stream, long long *launches);
 

@@ -1,0 +1,223 @@
+/* Stand-alone host driver of cpic_b200: cpic's command line (`cpic [-q] <conf>`, reference
+ * src/cpic.c:50-191), run loop with the sampling statistics (src/sim.c:440-479, 621-654) and
+ * field output layout (src/output.c:401-635), over the C ABI. Nothing here is on the
+ * per-timestep path except the call to cpic_b200_step. */
+#include <errno.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/stat.h>
+#include <time.h>
+#include <unistd.h>
+
+#include <string>
+#include <vector>
+
+#include "cpic_b200.h"
+#include "front.h"
+
+static int
+mkdir_ok(const std::string &p)
+{
+	if(mkdir(p.c_str(), 0700) && errno != EEXIST)
+	{
+		front_set_error("mkdir %s: %s", p.c_str(), strerror(errno));
+		return -1;
+	}
+	return 0;
+}
+
+/* write_field, reference src/output.c:482-590: the padded array as it is, rounded up to
+ * whole `alignment` blocks (the reference's allocation pads with 0xca, src/mat.c:116) */
+static int
+write_field(cpic_b200_sim_t *sim, int field, const std::string &file, int64_t alignment,
+		int64_t *rows_out, int64_t *stride_out)
+{
+	int64_t rows, stride;
+	if(cpic_b200_field_shape(sim, field, &rows, &stride)) return -1;
+	const size_t bytes = (size_t) rows * stride * sizeof(double);
+	const size_t total = (bytes + alignment - 1) / alignment * alignment;
+	std::vector<unsigned char> buf(total, 0xca);
+	if(cpic_b200_get_field(sim, field, (double *) buf.data())) return -1;
+	FILE *f = fopen(file.c_str(), "wb");
+	if(!f || fwrite(buf.data(), 1, total, f) != total)
+	{
+		front_set_error("cannot write %s: %s", file.c_str(), strerror(errno));
+		if(f) fclose(f);
+		return -1;
+	}
+	fclose(f);
+	*rows_out = rows;
+	*stride_out = stride;
+	return 0;
+}
+
+/* write_field_attribute, reference src/output.c:401-421 */
+static void
+xdmf_attribute(FILE *f, long iter, const char *name, long nx, long ny, long dy, long rows, long stride)
+{
+	fprintf(f, "      <Attribute Center=\"Node\" Name=\"%s\" DataType=\"Scalar\">\n", name);
+	fprintf(f, "        <DataItem ItemType=\"HyperSlab\" Dimensions=\"1 %ld %ld\" Type=\"HyperSlab\">\n", ny, nx);
+	fprintf(f, "          <DataItem Dimensions=\"3 3\" Format=\"XML\">\n");
+	fprintf(f, "            0 %ld %ld\n", dy, 0L);
+	fprintf(f, "            1 1 1\n");
+	fprintf(f, "            1 %ld %ld\n", dy + ny, nx);
+	fprintf(f, "          </DataItem>\n");
+	fprintf(f, "          <DataItem Dimensions=\"1 %ld %ld\" DataType=\"Float\" Precision=\"8\" Format=\"Binary\">\n", rows, stride);
+	fprintf(f, "            ../bin/%ld/%s.bin\n", iter, name);
+	fprintf(f, "          </DataItem>\n");
+	fprintf(f, "        </DataItem>\n");
+	fprintf(f, "      </Attribute>\n");
+}
+
+/* output_fields, reference src/output.c:594-635 and write_xdmf_fields :423-460 */
+extern "C" int
+cpic_b200_write_fields(cpic_b200_sim_t *sim, const char *path, int64_t iter, int64_t alignment,
+		int64_t nx, int64_t ny, double dx, double dy)
+{
+	if(!sim || !path) { front_set_error("null argument"); return CPIC_B200_EINVAL; }
+	if(alignment <= 0) alignment = 512;
+	const std::string root(path);
+	if(mkdir_ok(root) || mkdir_ok(root + "/xdmf") || mkdir_ok(root + "/bin")) return CPIC_B200_EINVAL;
+	const std::string dir = root + "/bin/" + std::to_string(iter);
+	if(mkdir_ok(dir)) return CPIC_B200_EINVAL;
+
+	int64_t rows[4], stride[4];
+	const char *names[4] = { "rho", "phi", "E_X", "E_Y" };
+	const int fields[4] = { CPIC_B200_RHO, CPIC_B200_PHI, CPIC_B200_EX, CPIC_B200_EY };
+	for(int k = 0; k < 4; k++)
+		if(write_field(sim, fields[k], dir + "/" + names[k] + ".bin", alignment, &rows[k], &stride[k]))
+			return CPIC_B200_EINVAL;
+
+	const std::string xf = root + "/xdmf/fields-iter" + std::to_string(iter) + ".xdmf";
+	FILE *f = fopen(xf.c_str(), "w");
+	if(!f) { front_set_error("cannot write %s", xf.c_str()); return CPIC_B200_EINVAL; }
+	fprintf(f, "<?xml version=\"1.0\" encoding=\"utf-8\"?>\n");
+	fprintf(f, "<Xdmf xmlns:xi=\"http://www.w3.org/2001/XInclude\" Version=\"3.0\">\n");
+	fprintf(f, "  <Domain>\n");
+	fprintf(f, "    <Grid Name=\"fields\">\n");
+	fprintf(f, "      <Topology TopologyType=\"3DCoRectMesh\" NumberOfElements=\"%ld %ld %ld\"/>\n", 1L, (long) ny, (long) nx);
+	fprintf(f, "      <Geometry Origin=\"\" Type=\"ORIGIN_DXDYDZ\">\n");
+	fprintf(f, "        <DataItem Format=\"XML\" Dimensions=\"3\">\n");
+	fprintf(f, "            0.0 0.0 0.0\n");
+	fprintf(f, "        </DataItem>\n");
+	fprintf(f, "        <DataItem Format=\"XML\" Dimensions=\"3\">\n");
+	fprintf(f, "            %f %f %f\n", 0.0, dy, dx);
+	fprintf(f, "        </DataItem>\n");
+	fprintf(f, "      </Geometry>\n");
+	/* phi is a view one row into `_phi` (PHI_NG_NORTH, reference src/def.h:11, src/field.c:96) */
+	xdmf_attribute(f, (long) iter, "phi", (long) nx, (long) ny, 1, (long) rows[1], (long) stride[1]);
+	xdmf_attribute(f, (long) iter, "rho", (long) nx, (long) ny, 0, (long) rows[0], (long) stride[0]);
+	xdmf_attribute(f, (long) iter, "E_X", (long) nx, (long) ny, 0, (long) rows[2], (long) stride[2]);
+	xdmf_attribute(f, (long) iter, "E_Y", (long) nx, (long) ny, 0, (long) rows[3], (long) stride[3]);
+	fprintf(f, "    </Grid>\n");
+	fprintf(f, "  </Domain>\n");
+	fprintf(f, "</Xdmf>\n");
+	fclose(f);
+	return 0;
+}
+
+static double
+now(void)
+{
+	struct timespec t;
+	clock_gettime(CLOCK_MONOTONIC, &t);
+	return (double) t.tv_sec + 1e-9 * (double) t.tv_nsec;
+}
+
+/* main of cpic (reference src/cpic.c:50-191) + sim_run (src/sim.c:621-654) */
+extern "C" int
+cpic_b200_main(int argc, char **argv)
+{
+	int opt;
+	optind = 1;
+	while((opt = getopt(argc, argv, "qd")) != -1)
+	{
+		if(opt != 'q' && opt != 'd')
+		{
+			fprintf(stderr, "Simulation of plasma using particle in cell method (cpic_b200).\n\nUsage: %s [-q] <config file>\n", argv[0]);
+			return 1;
+		}
+	}
+	if(optind != argc - 1)
+	{
+		fprintf(stderr, "Simulation of plasma using particle in cell method (cpic_b200).\n\nUsage: %s [-q] <config file>\n", argv[0]);
+		return 1;
+	}
+	const char *fn = argv[optind];
+	const double t0 = now();
+	cpic_b200_sim_t *sim = NULL;
+	cpic_b200_run_t run;
+	cpic_b200_conf_t *conf = NULL;
+	cpic_b200_params_t p;
+	if(cpic_b200_conf_load(fn, &conf) || cpic_b200_conf_params(conf, 0, 1, -1, &p, &run))
+	{
+		fprintf(stderr, "Configuration read failed:\n%s\n", cpic_b200_last_error());
+		return 1;
+	}
+	cpic_b200_conf_free(conf);
+	if(!run.output_enabled) fprintf(stderr, "No output path specified, output will not be saved\n");
+	if(run.stop_SEM > 0.0) fprintf(stderr, "Sampling enabled with relative error limit %e\n", run.stop_SEM);
+	if(cpic_b200_sim_from_conf(fn, 0, 1, -1, 1, &sim, NULL))
+	{
+		fprintf(stderr, "sim_init failed\n%s\n", cpic_b200_last_error());
+		return 1;
+	}
+	printf("%e init-time\n", now() - t0);
+	printf("Simulation runs now\n");
+
+	/* Welford statistics of the iteration time, as perf_record/perf_stats (src/perf.c:85-133) */
+	double mean = 0.0, m2 = 0.0;
+	long n = 0;
+	const double dx = p.Lx / (double) p.nx, dy = p.Ly / (double) p.ny;
+	int running = 1;
+	while(running && cpic_b200_iter(sim) < run.cycles)
+	{
+		const double t1 = now();
+		/* sim_step writes the fields right after stage_field_E (src/sim.c:503-511) */
+		if(run.output_enabled)
+		{
+			if(cpic_b200_stage_field_E(sim)
+					|| cpic_b200_write_fields(sim, run.output_path, cpic_b200_iter(sim), run.output_alignment, p.nx, p.ny, dx, dy)
+					|| cpic_b200_stage_plasma_E(sim) || cpic_b200_stage_plasma_r(sim) || cpic_b200_stage_field_rho(sim)
+					|| cpic_b200_set_iter(sim, cpic_b200_iter(sim) + 1))
+			{
+				fprintf(stderr, "sim_step failed\n%s\n", cpic_b200_last_error());
+				return 1;
+			}
+		}
+		else if(cpic_b200_step(sim))
+		{
+			fprintf(stderr, "sim_step failed\n%s\n", cpic_b200_last_error());
+			return 1;
+		}
+		if(cpic_b200_sync(sim))
+		{
+			fprintf(stderr, "sim_step failed\n%s\n", cpic_b200_last_error());
+			return 1;
+		}
+		const double t = now() - t1;
+		if(run.stop_SEM > 0.0)
+		{
+			/* sampling_complete, src/sim.c:440-479 */
+			const double std = n > 1 ? sqrt(m2 / (double) (n - 1)) : 0.0;
+			const double sem = n > 0 ? std / sqrt((double) n) : 0.0;
+			n++;
+			const double d = t - mean;
+			mean += d / (double) n;
+			m2 += d * (t - mean);
+			const double rsem = mean != 0.0 ? sem / mean : sem;
+			printf("stats iter=%ld last=%e mean=%e std=%e sem=%e rsem=%e mem=%ld solver=%e\n",
+					(long) cpic_b200_iter(sim) - 1, t, mean, std, sem, rsem, 0L, 0.0);
+			if(cpic_b200_iter(sim) - 1 >= 30 && 1.96 * sem < run.stop_SEM * mean)
+			{
+				printf("sampling complete\n");
+				running = 0;
+			}
+		}
+	}
+	printf("Simulation ends\n");
+	cpic_b200_destroy(sim);
+	return 0;
+}

@@ -870,6 +870,8 @@ static int
 exchange(sim_t_ *s)
 {
 	StageTimer t(s, T_EXCHANGE);
+	SpeciesDev *sps[CPIC_B200_MAX_SPECIES];
+	int arrs[CPIC_B200_MAX_SPECIES], nsp = 0;
 	for(int is = 0; is < s->p.nspecies; is++)
 	{
 		SpeciesHost &h = s->sp[is];
@@ -878,12 +880,10 @@ exchange(sim_t_ *s)
 		k_far_insert<<<1, 1024, 0, s->stream>>>(h.d, s->g, s->errflag);
 		int rc = check_launch(s);
 		if(rc) return rc;
-		if(s->comm)
-		{
-			rc = comm_particles(s->comm, &h.d, h.arr, s->g, s->nb, s->stream, s->errflag, &s->launches);
-			if(rc) return rc;
-		}
+		sps[nsp] = &h.d;
+		arrs[nsp++] = h.arr;
 	}
+	if(s->comm && nsp) return comm_particles(s->comm, sps, arrs, nsp, s->g, s->nb, s->stream, s->errflag, &s->launches);
 	return 0;
 }
 

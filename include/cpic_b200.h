@@ -198,6 +198,13 @@ int cpic_b200_conf_init_particles(const cpic_b200_conf_t *conf, int ref_nprocs,
  * call cpic_b200_comm_init and cpic_b200_pre_step afterwards. */
 int cpic_b200_sim_from_conf(const char *path, int rank, int nranks, int device, int ref_nprocs,
 		cpic_b200_sim_t **sim, cpic_b200_run_t *run);
+/* output_fields (reference src/output.c:594-635): <path>/bin/<iter>/{rho,phi,E_X,E_Y}.bin -- the
+ * padded arrays as they are, rounded up to `alignment` bytes -- and
+ * <path>/xdmf/fields-iter<iter>.xdmf with the reference's hyperslab descriptors. */
+int cpic_b200_write_fields(cpic_b200_sim_t *sim, const char *path, int64_t iter, int64_t alignment,
+		int64_t nx, int64_t ny, double dx, double dy);
+/* The reference's command line, `cpic [-q] <conf>` (src/cpic.c:50-191), on one GPU */
+int cpic_b200_main(int argc, char **argv);
 
 #ifdef __cplusplus
 }

@@ -90,3 +90,38 @@ def test_reference_cli_and_output_layout(tmp_path):
             scale = np.abs(b[ok]).max()
             assert np.abs(a[ok] - b[ok]).max() <= 1e-12 * scale, (it, f)
         assert (outs["gpu"] / "xdmf" / f"fields-iter{it}.xdmf").exists()
+
+
+def test_own_cli_writes_the_reference_output_layout(tmp_path):
+    """The stand-alone driver (cpic_b200_cli, same usage as src/cpic.c) with output enabled
+    against the CPU reference's files: identical sizes (padded arrays rounded up to
+    output.alignment), values to 1e-12, and the same xdmf descriptors."""
+    cli = os.path.join(ROOT, "cpic_b200", "cpic_b200_cli")
+    ref = os.path.join(REF, "cpic_ref")
+    if not os.path.exists(ref):
+        pytest.skip("cpic_ref not built")
+    text = open(os.path.join(ROOT, "conf", "two-streams.conf")).read().replace("cycles = 800", "cycles = 4")
+    outs = {}
+    for name, binary in (("gpu", cli), ("cpu", ref)):
+        d = tmp_path / name
+        conf = tmp_path / f"{name}.conf"
+        conf.write_text(text + f'\noutput = {{ path = "{d}" slices = 4 alignment = 4096 }}\n')
+        r = subprocess.run([binary, "-q", str(conf)], cwd=ROOT, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:] + r.stdout[-500:]
+        outs[name] = d
+    nx = 64
+    for it in range(4):
+        for f in ("rho", "phi", "E_X", "E_Y"):
+            pa, pb = outs["gpu"] / "bin" / str(it) / f"{f}.bin", outs["cpu"] / "bin" / str(it) / f"{f}.bin"
+            assert os.path.getsize(pa) == os.path.getsize(pb) and os.path.getsize(pa) % 4096 == 0
+            a, b = np.fromfile(pa), np.fromfile(pb)
+            ok = np.isfinite(b) & (np.abs(b) < 1e300)
+            if f in ("rho", "phi"):
+                ok &= (np.arange(a.size) % (nx + 2)) < nx
+            n_live = {"rho": 65, "phi": 67, "E_X": 65, "E_Y": 65}[f] * (nx + 2 if f in ("rho", "phi") else nx)
+            ok &= np.arange(a.size) < n_live
+            assert ok.sum() > 0.9 * 64 * 64
+            assert np.abs(a[ok] - b[ok]).max() <= 1e-12 * np.abs(b[ok]).max(), (it, f)
+        xa = (outs["gpu"] / "xdmf" / f"fields-iter{it}.xdmf").read_text()
+        xb = (outs["cpu"] / "xdmf" / f"fields-iter{it}.xdmf").read_text()
+        assert xa == xb

@@ -127,3 +127,17 @@ def test_ref_nprocs_striping():
     first_a = a["x"][0:n:2][: n // 4]
     first_b = b["x"][0:n:4][: n // 4]
     assert np.array_equal(first_a, first_b)
+
+
+def test_cli_usage_and_no_gpu_message():
+    """cpic_b200_cli keeps the reference's command line (src/cpic.c:30-38, :114-127)."""
+    import subprocess
+    cli = os.path.join(ROOT, "cpic_b200", "cpic_b200_cli")
+    r = subprocess.run([cli], capture_output=True, text=True)
+    assert r.returncode == 1 and "Usage:" in r.stderr and "<config file>" in r.stderr
+    r = subprocess.run([cli, "-q", "/nonexistent.conf"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Configuration read failed" in r.stderr
+    import torch
+    if not torch.cuda.is_available():
+        r = subprocess.run([cli, "-q", conf_path("cyclotron.conf")], capture_output=True, text=True)
+        assert r.returncode == 1 and "no CPU path" in r.stderr
