@@ -233,14 +233,15 @@ def main():
     n_total = n_rank * world
 
     sim = Sim(params)
-    if world == 1 and args.workload == "A":
+    if world == 1 and args.workload == "A" and "BENCH_VSCALE" not in os.environ:
         # the reference's own initial conditions (glibc rand() stream, src/particle.c:23-89)
         parts = init_particles(conf)
         for i, p in enumerate(parts):
             sim.set_particles(i, p["id"], p["x"], p["y"], p["ux"], p["uy"])
         data = "synthetic (reference initialiser: uniform random positions, u~U(-v,v), seed 138)"
     else:
-        drift = [(5.0, 0.0), (3.0, 0.0)]
+        vs = float(os.environ.get("BENCH_VSCALE", "1.0"))     # experiments: colder / hotter plasma
+        drift = [(5.0 * vs, 0.0), (3.0 * vs, 0.0)]
         for i in range(nspecies):
             sim.init_uniform(i, nps, id0=rank * nps, vx=drift[i][0], vy=drift[i][1], seed=138 + i)
         data = "synthetic (device initialiser: uniform positions per particle block, u~U(-v,v))"
@@ -288,6 +289,21 @@ def main():
     stage_ms, launches = sim.get_timing()
     dbg("stage timing done")
     sim.timing(False)
+    # the reference's separate stages (stage_plasma_E, stage_plasma_r): gather-only and push-only kernels
+    staged = None
+    if world == 1:
+        sim.step_staged()            # allocates the per-particle E arrays: not timed
+        sim.sync()
+        sim.timing(True)
+        ns = max(3, min(args.steps, 10))
+        for _ in range(ns):
+            sim.step_staged()
+        sim.sync()
+        st_ms, _ = sim.get_timing()
+        sim.timing(False)
+        staged = {"steps": ns, "gather_ms_per_launch": st_ms["gather"] / (ns * nspecies),
+                  "push_ms_per_launch": st_ms["gather_push"] / (ns * nspecies),
+                  "deposit_ms_per_launch": st_ms["field_rho"] / (ns * nspecies)}
     # the same count on every rank (the steps contain collectives)
     reps = int(min(60, max(0, (1500.0 - (time.perf_counter() - t_clk) * 1e3) / max(ms, 1e-3))))
     r_t = torch.tensor([reps], dtype=torch.int64, device="cuda")
@@ -317,6 +333,18 @@ def main():
                 "avg_launch_ms": t_push,
                 "whole_step_frac": (n_rank * args.steps / (ms * 1e-3)) * (BYTES_GATHER_PUSH + BYTES_DEPOSIT) / 1e9 / peak,
                 "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()}}
+    if staged:
+        gb = lambda nbytes, ms_: nbytes * nps / (ms_ * 1e-3) / 1e9 if ms_ > 0 else 0.0
+        roofline["other_kernels"] = {
+            "k_gather_push<0> (gather, 32 B/particle)": {"avg_launch_ms": staged["gather_ms_per_launch"],
+                                                          "achieved": gb(32.0, staged["gather_ms_per_launch"]),
+                                                          "frac": gb(32.0, staged["gather_ms_per_launch"]) / peak},
+            "k_gather_push<1> (push + exchange, 96 B/particle)": {"avg_launch_ms": staged["push_ms_per_launch"],
+                                                                   "achieved": gb(96.0, staged["push_ms_per_launch"]),
+                                                                   "frac": gb(96.0, staged["push_ms_per_launch"]) / peak},
+            "k_deposit (+stitch, 16 B/particle)": {"avg_launch_ms": t_dep / nspecies,
+                                                    "achieved": gb(16.0, t_dep / nspecies),
+                                                    "frac": gb(16.0, t_dep / nspecies) / peak}}
 
     # ---- e2e: the same K steps with the particle state living in pinned HOST memory: every step
     # uploads it, runs one sim_step through the C ABI, and reads back particles and the four grids

@@ -79,7 +79,7 @@ EXPORTS = {
     "cpic_b200_solve": (_i, [_vp]),
     "cpic_b200_energy": (_i, [_vp, C.POINTER(_d), C.POINTER(_d)]),
     "cpic_b200_timing": (_i, [_vp, _i]),
-    "cpic_b200_get_timing": (_i, [_vp, C.POINTER(_d * 5), C.POINTER(_i64)]),
+    "cpic_b200_get_timing": (_i, [_vp, C.POINTER(_d * 6), C.POINTER(_i64)]),
     "cpic_b200_image_bytes": (_i64, [_vp]),
     "cpic_b200_image_download": (_i, [_vp, _vp, _i64]),
     "cpic_b200_image_upload": (_i, [_vp, _vp, _i64]),

@@ -836,14 +836,18 @@ k_absorb(SpeciesDev sp, Geom g, int nb, int arr, int *__restrict__ errflag)
 
 /* interpolate_p2f_rho, reference src/interpolate.c:282-346 / :161-276, accumulate-correct.
  * Each warp sums its block's particles (own segment, then the arrivals in outbox `arr`)
- * into a private (BY+1) x (BX+1) tile in shared memory. Per batch of 32, lanes that share
- * a cell are ranked in lane order (match_any); rank r adds in round r, and inside a round
- * the four corners are added in four phases: within a phase distinct cells hit distinct
- * nodes, so plain read-modify-write is race free and every node's sum has a fixed order
- * (batch, rank, corner). The CTA then merges its WPC tiles left to right and stores:
- * interior nodes to rho (`=` for the first species, `+=` after), bottom row / right
- * column / corner to the halo arrays that k_stitch_* add in a fixed order. rho_reset
- * (src/field.c:163-210) is implicit. */
+ * into private accumulators in shared memory: DEP_REP replicas (lane l uses replica
+ * l % DEP_REP) of four arrays indexed by CELL, one per corner weight (w00, w01, w10, w11).
+ * Two lanes can then only meet when they hold particles of the same cell in the same
+ * replica; such lanes are ranked in lane order (match_any) and rank r adds in round r --
+ * plain read-modify-write, race free, four independent updates per lane and round. Every
+ * accumulator therefore has a fixed order of additions (batch, rank). The CTA finally
+ * forms every node of its tile as the fixed-order sum of the (up to four) cells around it,
+ * replicas in order, left block before right block, and stores: interior nodes to rho
+ * (`=` for the first species, `+=` after), bottom row / right column / corner to the halo
+ * arrays that k_stitch_* add in a fixed order. rho_reset (src/field.c:163-210) is implicit. */
+#define DEP_REP 2
+
 template <bool FIRST>
 __global__ void __launch_bounds__(32 * MAX_WPC)
 k_deposit(SpeciesDev sp, Geom g, double vq, int nb, int arr,
@@ -851,8 +855,9 @@ k_deposit(SpeciesDev sp, Geom g, double vq, int nb, int arr,
 		double *__restrict__ hc)
 {
 	extern __shared__ __align__(128) unsigned char smem[];
-	double *tiles = (double *) smem;
-	const int TWd = g.BX + 1, THd = g.BY + 1, tsz = TWd * THd;
+	double *acc = (double *) smem;
+	const int NC = g.BX * g.BY;                  /* cells per block */
+	const int wsz = DEP_REP * 4 * NC;            /* accumulators per warp: [replica][corner][cell] */
 
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const unsigned lt = (1u << lane) - 1;
@@ -860,7 +865,7 @@ k_deposit(SpeciesDev sp, Geom g, double vq, int nb, int arr,
 	const int by = blockIdx.x / ncx, cx = blockIdx.x % ncx;
 	const int bx = cx * g.WPC + warp;
 	const int b = by * g.nbx + bx;
-	double *t = tiles + warp * tsz;
+	double *t = acc + warp * wsz + (lane % DEP_REP) * 4 * NC;
 
 	__shared__ int scratch[MAX_WPC][18];
 	const Outbox &in = sp.ob[arr];
@@ -877,7 +882,7 @@ k_deposit(SpeciesDev sp, Geom g, double vq, int nb, int arr,
 		else { const size_t so = arrival_slot(A, sp, lane - cnt); px = in.x[so]; py = in.y[so]; }
 	}
 
-	for(int k = lane; k < tsz; k += 32) t[k] = 0.0;
+	for(int k = lane; k < wsz; k += 32) acc[warp * wsz + k] = 0.0;
 	__syncwarp();
 
 	for(int i0 = 0; i0 < T; i0 += 32)
@@ -891,8 +896,8 @@ k_deposit(SpeciesDev sp, Geom g, double vq, int nb, int arr,
 			else { const size_t so = arrival_slot(A, sp, i + 32 - cnt); px = in.x[so]; py = in.y[so]; }
 		}
 
-		int cell = -1 - lane;         /* unique key for idle lanes */
-		int node = 0;
+		int key = -1 - lane;          /* unique key for idle lanes */
+		int cell = 0;
 		double a00 = 0, a01 = 0, a10 = 0, a11 = 0;
 		if(valid)
 		{
@@ -900,40 +905,57 @@ k_deposit(SpeciesDev sp, Geom g, double vq, int nb, int arr,
 			double w00, w01, w10, w11;
 			cic_weights(g, x, y, i0x, i0y, w00, w01, w10, w11);
 			a00 = MUL(w00, vq); a01 = MUL(w01, vq); a10 = MUL(w10, vq); a11 = MUL(w11, vq);
-			node = (i0y - cy0) * TWd + (i0x - cx0);
-			cell = node;
+			cell = ((i0y - cy0) << g.lBX) + (i0x - cx0);
+			key = cell * DEP_REP + lane % DEP_REP;
 		}
-		const unsigned peers = __match_any_sync(FULL, cell);
+		const unsigned peers = __match_any_sync(FULL, key);
 		const int rank = __popc(peers & lt);
 		const int rounds = __reduce_max_sync(FULL, valid ? rank + 1 : 0);
 		for(int r = 0; r < rounds; r++)
 		{
-			const bool add = valid && rank == r;
-			if(add) t[node] += a00;
-			__syncwarp();
-			if(add) t[node + TWd] += a01;
-			__syncwarp();
-			if(add) t[node + 1] += a10;
-			__syncwarp();
-			if(add) t[node + TWd + 1] += a11;
+			if(valid && rank == r)
+			{
+				const double v0 = t[cell], v1 = t[NC + cell], v2 = t[2 * NC + cell], v3 = t[3 * NC + cell];
+				t[cell] = ADD(v0, a00);
+				t[NC + cell] = ADD(v1, a01);
+				t[2 * NC + cell] = ADD(v2, a10);
+				t[3 * NC + cell] = ADD(v3, a11);
+			}
 			__syncwarp();
 		}
 	}
 
 	__syncthreads();
 
-	/* merge the WPC private tiles and store */
-	const int W = g.WPC * g.BX;
+	/* every node of the CTA tile from the cells around it. Block-local node (lr, lc), lr in
+	 * [0, BY], lc in [0, BX]: corner (a, b) of cell (lc - a, lr - b) when that cell exists;
+	 * corner arrays: 0 = w00 (0,0), 1 = w01 (0,+1), 2 = w10 (+1,0), 3 = w11 (+1,+1). */
+	const int W = g.WPC * g.BX, THd = g.BY + 1;
 	for(int k = threadIdx.x; k < THd * (W + 1); k += blockDim.x)
 	{
 		const int r = k / (W + 1), c = k % (W + 1);
-		const int w = c / g.BX, j = c % g.BX;
-		double v;
-		if(c == W) v = tiles[(g.WPC - 1) * tsz + r * TWd + g.BX];
-		else
+		double v = 0.0;
+		/* the block whose column range holds c contributes its left corners (a = 0); the block
+		 * to the left contributes its right corners (a = 1) */
+#pragma unroll
+		for(int side = 0; side < 2; side++)
 		{
-			v = tiles[w * tsz + r * TWd + j];
-			if(j == 0 && w > 0) v += tiles[(w - 1) * tsz + r * TWd + g.BX];
+			const int a = side == 0 ? 1 : 0;                       /* left block first */
+			const int w = (c - a) >= 0 ? (c - a) >> g.lBX : -1;
+			if(w < 0 || w >= g.WPC) continue;
+			const int lx = (c - a) - (w << g.lBX);
+			const double *tw = acc + w * wsz;
+#pragma unroll
+			for(int bb = 0; bb < 2; bb++)
+			{
+				const int ly = r - bb;
+				if(ly < 0 || ly >= g.BY) continue;
+				const int cell = (ly << g.lBX) + lx;
+				const int corner = a * 2 + bb;
+#pragma unroll
+				for(int rep = 0; rep < DEP_REP; rep++)
+					v = ADD(v, tw[rep * 4 * NC + corner * NC + cell]);
+			}
 		}
 		double *dst;
 		if(r < g.BY && c < W) dst = rho + (size_t) (by * g.BY + r) * g.S + (size_t) cx * W + c;

@@ -58,7 +58,7 @@ struct SpeciesHost {
 	double q, m;
 };
 
-enum { T_FIELD_E, T_PUSH, T_EXCHANGE, T_RHO, T_SOLVER, T_COUNT };
+enum { T_FIELD_E, T_PUSH, T_EXCHANGE, T_RHO, T_SOLVER, T_GATHER, T_COUNT };
 
 struct cpic_b200_sim {
 	cpic_b200_params_t p;
@@ -285,7 +285,7 @@ cpic_b200_create(const cpic_b200_params_t *pp, cpic_b200_sim_t **out)
 	/* barrier + per-warp scratch + two E tiles + per-warp prefetch rings (sized for the
 	 * widest mode: 8 arrays) */
 	s->smem_push = PUSH_SMEM_HEADER + MAX_WPC * 32 * sizeof(int) + 2 * tile_bytes(g);
-	s->smem_dep = (size_t) g.WPC * (g.BX + 1) * (g.BY + 1) * sizeof(double);
+	s->smem_dep = (size_t) g.WPC * DEP_REP * 4 * g.BX * g.BY * sizeof(double);
 
 	for(int i = 0; i < p.nspecies; i++) { s->sp[i].q = p.q[i]; s->sp[i].m = p.m[i]; }
 
@@ -731,7 +731,7 @@ cpic_b200_timing(cpic_b200_sim_t *s, int enable)
 }
 
 extern "C" int
-cpic_b200_get_timing(cpic_b200_sim_t *s, double ms[5], int64_t launches[1])
+cpic_b200_get_timing(cpic_b200_sim_t *s, double ms[6], int64_t launches[1])
 {
 	if(!s) return fail(CPIC_B200_EINVAL, "null sim");
 	if(ms) for(int i = 0; i < T_COUNT; i++) ms[i] = s->ms[i];
@@ -851,7 +851,7 @@ cpic_b200_stage_plasma_E(cpic_b200_sim_t *s)
 {
 	if(!s) return fail(CPIC_B200_EINVAL, "null sim");
 	CK(cudaSetDevice(s->device));
-	StageTimer t(s, T_PUSH);
+	StageTimer t(s, T_GATHER);
 	for(int is = 0; is < s->p.nspecies; is++)
 	{
 		int rc = ensure_particle_E(s, is);
@@ -924,10 +924,12 @@ cpic_b200_stage_field_rho(cpic_b200_sim_t *s)
 	const int ctas = s->nb / g.WPC;
 	const int ncx = g.nbx / g.WPC;
 	bool first = true;
-	if(s->smem_dep > 48 * 1024)
+	static size_t dep_attr = 0;
+	if(s->smem_dep > dep_attr)
 	{
 		CK(cudaFuncSetAttribute(k_deposit<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) s->smem_dep));
 		CK(cudaFuncSetAttribute(k_deposit<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) s->smem_dep));
+		dep_attr = s->smem_dep;
 	}
 	for(int is = 0; is < s->p.nspecies; is++)
 	{

@@ -294,7 +294,7 @@ class Sim:
         check(self.L.cpic_b200_timing(self.h, int(enable)))
 
     def get_timing(self):
-        ms = (C.c_double * 5)()
+        ms = (C.c_double * 6)()
         n = C.c_int64()
         check(self.L.cpic_b200_get_timing(self.h, C.byref(ms), C.byref(n)))
-        return dict(zip(("field_E", "gather_push", "exchange", "field_rho", "solver"), ms)), n.value
+        return dict(zip(("field_E", "gather_push", "exchange", "field_rho", "solver", "gather"), ms)), n.value

@@ -145,10 +145,12 @@ int cpic_b200_energy(cpic_b200_sim_t *sim, double *kinetic, double *potential);
 
 /* ---- measurement ---- */
 /* Device time (ms, CUDA events on the simulation's stream) spent in each stage since the
- * last reset: [0] field_E [1] plasma_E+plasma_r (gather+push) [2] particle exchange
- * [3] field_rho [4] solver alone. Enable with cpic_b200_timing(sim, 1). */
+ * last reset: [0] field_E without the solver [1] the push kernels (fused gather+push in
+ * cpic_b200_step, push alone in stage_plasma_r) [2] particle exchange [3] field_rho
+ * [4] solver alone [5] the gather kernels of stage_plasma_E. Enable with
+ * cpic_b200_timing(sim, 1). */
 int cpic_b200_timing(cpic_b200_sim_t *sim, int enable);
-int cpic_b200_get_timing(cpic_b200_sim_t *sim, double ms[5], int64_t launches[1]);
+int cpic_b200_get_timing(cpic_b200_sim_t *sim, double ms[6], int64_t launches[1]);
 
 /* Compact particle image for host<->device round trips (bench e2e, checkpoints): the live
  * particles of every block, block after block, with the block counts. The caller owns a
