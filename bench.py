@@ -198,6 +198,8 @@ def main():
     ap.add_argument("--workload", default="A", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--strong", action="store_true",
+                    help="strong scaling: the workload's grid and particles are divided over the GPUs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -220,6 +222,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     name, nx, ny, nps = WORKLOADS[args.workload]
+    if args.strong:
+        ny, nps = ny // world, nps // world          # per GPU: a slab of the fixed global problem
     conf = os.path.join(ROOT, "conf", name)
     params, run = load_conf(conf, rank=rank, nranks=world, device=local)
     params.nx, params.ny = nx, ny * world        # weak scaling: one nx x ny slab per GPU
@@ -390,7 +394,7 @@ def main():
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": data,
+                "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f64", "data": data,
                 "config": {"workload": f"{name}: {nx}x{ny} grid and {n_rank} particles per GPU "
                                        f"({params.nx}x{params.ny}, {n_total} particles in total), 2 species, "
                                        f"B=(0,0,-0.2), dt=5e-3",

@@ -232,6 +232,8 @@ comm_phi_halo(Comm *c, double *phi, cudaStream_t stream)
 	return 0;
 }
 
+#define FAR_SECTION (1 + 8 * FAR_FACE)      /* doubles: count, then eight arrays */
+
 /* Pack / unpack of the regions that cross a slab face. A face buffer holds, for the three
  * codes k of that direction and the NA arrays (x y ux uy uz id [Ex Ey]), the regions of
  * the nbx edge blocks (nbx * rcap[code] values each), followed by the 3 * nbx counts. */
@@ -314,7 +316,6 @@ int
 comm_particles(Comm *c, SpeciesDev *const *sps, const int *arrs, int nsp, const Geom &g, int nb,
 		cudaStream_t stream, int *errflag, long long *launches)
 {
-	(void) errflag;
 	const int south = (c->rank + 1) % c->n, north = (c->rank + c->n - 1) % c->n;
 	const int nbx = g.nbx;
 	FaceLayout Ln[8], Ls[8];
@@ -324,8 +325,8 @@ comm_particles(Comm *c, SpeciesDev *const *sps, const int *arrs, int nsp, const 
 	{
 		Ln[i] = face_layout(sps[i], nbx, 0);
 		Ls[i] = face_layout(sps[i], nbx, 6);
-		/* both layouts have the same size (corner, side, corner) */
-		off[i + 1] = off[i] + (size_t) Ln[i].total + (3 * (size_t) nbx + 1) / 2;
+		/* both layouts have the same size (corner, side, corner); then the far-mover section */
+		off[i + 1] = off[i] + (size_t) Ln[i].total + (3 * (size_t) nbx + 1) / 2 + FAR_SECTION;
 	}
 	const size_t doubles = off[nsp];
 	if(doubles > c->face_cap)
@@ -341,6 +342,8 @@ comm_particles(Comm *c, SpeciesDev *const *sps, const int *arrs, int nsp, const 
 		const int blocks = (int) ((threads + 255) / 256);
 		k_face_copy<<<blocks, 256, 0, stream>>>(*sps[i], arrs[i], nbx, 0, 0, Ln[i], send_n + off[i], 1);
 		k_face_copy<<<blocks, 256, 0, stream>>>(*sps[i], arrs[i], nbx, nb - nbx, 6, Ls[i], send_s + off[i], 1);
+		k_far_face<<<1, 256, 0, stream>>>(*sps[i], 0, send_n + off[i + 1] - FAR_SECTION, 1, errflag);
+		k_far_face<<<1, 256, 0, stream>>>(*sps[i], 1, send_s + off[i + 1] - FAR_SECTION, 1, errflag);
 	}
 	NCK(g_nccl.GroupStart());
 	NCK(g_nccl.Send(send_n, doubles, ncclFloat64, north, c->nc, stream));
@@ -355,9 +358,11 @@ comm_particles(Comm *c, SpeciesDev *const *sps, const int *arrs, int nsp, const 
 		const int blocks = (int) ((threads + 255) / 256);
 		k_face_copy<<<blocks, 256, 0, stream>>>(*sps[i], arrs[i], nbx, nb + nbx, 0, Ln[i], recv_s + off[i], 0);
 		k_face_copy<<<blocks, 256, 0, stream>>>(*sps[i], arrs[i], nbx, nb, 6, Ls[i], recv_n + off[i], 0);
+		k_far_face<<<1, 256, 0, stream>>>(*sps[i], 0, recv_s + off[i + 1] - FAR_SECTION, 0, errflag);
+		k_far_face<<<1, 256, 0, stream>>>(*sps[i], 1, recv_n + off[i + 1] - FAR_SECTION, 0, errflag);
 	}
 	CCK(cudaGetLastError());
-	if(launches) *launches += 4 * nsp;
+	if(launches) *launches += 8 * nsp;
 	return 0;
 }
 

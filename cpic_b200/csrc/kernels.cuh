@@ -58,9 +58,14 @@ struct SpeciesDev {
 	long long *fkey;         /* sort scratch: (destination block, id) */
 	int *fidx;
 	int *fcount;
+	/* far movers that belong to the north [0] / south [1] neighbour rank: FAR_FACE entries of
+	 * eight values (x y ux uy uz id Ex Ey, array-major), sent with the particle faces */
+	double *rfar[2];
+	int *rfcount;            /* [2] */
 };
 
 #define FAR_CAP 65536
+#define FAR_FACE 2048
 
 /* Slot of entry `pos` in the region (block b, destination code c) */
 __device__ __forceinline__ unsigned
@@ -720,7 +725,8 @@ k_far_insert(SpeciesDev sp, Geom g, int *__restrict__ errflag)
 	while(m < n) m <<= 1;
 	long long *key = m <= FAR_SMEM ? skey : sp.fkey;
 	int *idx = m <= FAR_SMEM ? sidx : sp.fidx;
-	const long long OUT = 0x7ffffffffffffffeLL, PAD = 0x7fffffffffffffffLL;
+	/* keys: local destinations (block << 40 | id) < REMOTE <= north rank < south rank < OUT */
+	const long long REMOTE = 1LL << 62, OUT = 0x7ffffffffffffffeLL, PAD = 0x7fffffffffffffffLL;
 	for(int i = threadIdx.x; i < m; i += blockDim.x)
 	{
 		long long k = PAD;
@@ -728,8 +734,18 @@ k_far_insert(SpeciesDev sp, Geom g, int *__restrict__ errflag)
 		{
 			const double x = sp.fx[i], y = sp.fy[i];
 			const int row = global_row(g, y);
-			if(row < g.row0 || row >= g.row0 + g.ny) { k = OUT; atomicOr(errflag, ERRBIT_FAR); }
-			else k = ((long long) block_of(g, x, y) << 40) | (sp.fid[i] & 0xffffffffffLL);
+			const long long pid = sp.fid[i] & 0xffffffffffLL;
+			if(row >= g.row0 && row < g.row0 + g.ny)
+				k = ((long long) block_of(g, x, y) << 40) | pid;
+			else
+			{
+				/* rows to walk north from the slab's first row / south from its last row */
+				const int dn = (g.row0 - row + g.ny_glob) % g.ny_glob;
+				const int ds = (row - (g.row0 + g.ny - 1) + g.ny_glob) % g.ny_glob;
+				const int dir = dn <= ds ? 0 : 1;
+				if((dir == 0 ? dn : ds) > g.ny || g.ny_glob == g.ny) { k = OUT; atomicOr(errflag, ERRBIT_FAR); }
+				else k = REMOTE | ((long long) dir << 60) | pid;
+			}
 		}
 		key[i] = k;
 		idx[i] = i;
@@ -740,11 +756,11 @@ k_far_insert(SpeciesDev sp, Geom g, int *__restrict__ errflag)
 	for(int i = threadIdx.x; i < n; i += blockDim.x)
 	{
 		const long long k = key[i];
-		if(k >= OUT) continue;
+		if(k >= REMOTE) continue;
 		const int b = (int) (k >> 40);
 		if(i > 0 && (int) (key[i - 1] >> 40) == b) continue;
 		int pos = sp.count[b];
-		for(int j = i; j < n && (int) (key[j] >> 40) == b && key[j] < OUT; j++)
+		for(int j = i; j < n && key[j] < REMOTE && (int) (key[j] >> 40) == b; j++)
 		{
 			if(pos >= sp.cap) { atomicOr(errflag, ERRBIT_ABSORB); break; }
 			const int e = idx[j];
@@ -757,8 +773,66 @@ k_far_insert(SpeciesDev sp, Geom g, int *__restrict__ errflag)
 		}
 		sp.count[b] = pos;
 	}
+	/* particles for the neighbour ranks, in id order, into the lists that travel with the
+	 * particle faces (comm.cu) */
+	if(threadIdx.x == 0)
+	{
+		int cn[2] = { sp.rfcount[0], sp.rfcount[1] };
+		for(int j = 0; j < n; j++)
+		{
+			const long long k = key[j];
+			if(k < REMOTE || k >= OUT) continue;
+			const int dir = (int) ((k >> 60) & 1);
+			if(cn[dir] >= FAR_FACE) { atomicOr(errflag, ERRBIT_FARLIST); continue; }
+			const int e = idx[j];
+			double *o = sp.rfar[dir] + cn[dir];
+			o[0 * FAR_FACE] = sp.fx[e]; o[1 * FAR_FACE] = sp.fy[e];
+			o[2 * FAR_FACE] = sp.fux[e]; o[3 * FAR_FACE] = sp.fuy[e]; o[4 * FAR_FACE] = sp.fuz[e];
+			o[5 * FAR_FACE] = __longlong_as_double(sp.fid[e]);
+			o[6 * FAR_FACE] = sp.fEx[e]; o[7 * FAR_FACE] = sp.fEy[e];
+			cn[dir]++;
+		}
+		sp.rfcount[0] = cn[0];
+		sp.rfcount[1] = cn[1];
+	}
 	__syncthreads();
 	if(threadIdx.x == 0) *sp.fcount = 0;
+}
+
+/* Far movers across a slab face. pack != 0: the list for direction `dir` goes into the
+ * face buffer section `buf` ([count as double][8 x FAR_FACE values]) and is emptied; else the
+ * section received from a neighbour is appended to the local far-mover list, which the next
+ * k_far_insert places. */
+static __global__ void __launch_bounds__(256)
+k_far_face(SpeciesDev sp, int dir, double *__restrict__ buf, int pack, int *__restrict__ errflag)
+{
+	__shared__ int base;
+	if(pack)
+	{
+		const int n = sp.rfcount[dir];
+		for(int i = threadIdx.x; i < 8 * FAR_FACE; i += blockDim.x)
+			if(i % FAR_FACE < n) buf[1 + i] = sp.rfar[dir][i];
+		__syncthreads();
+		if(threadIdx.x == 0) { buf[0] = (double) n; sp.rfcount[dir] = 0; }
+		return;
+	}
+	const int n = (int) buf[0];
+	if(threadIdx.x == 0) base = atomicAdd(sp.fcount, n);
+	__syncthreads();
+	if(base + n > FAR_CAP)
+	{
+		if(threadIdx.x == 0) atomicOr(errflag, ERRBIT_FARLIST);
+		return;
+	}
+	for(int i = threadIdx.x; i < n; i += blockDim.x)
+	{
+		const double *e = buf + 1 + i;
+		const int k = base + i;
+		sp.fx[k] = e[0 * FAR_FACE]; sp.fy[k] = e[1 * FAR_FACE];
+		sp.fux[k] = e[2 * FAR_FACE]; sp.fuy[k] = e[3 * FAR_FACE]; sp.fuz[k] = e[4 * FAR_FACE];
+		sp.fid[k] = __double_as_longlong(e[5 * FAR_FACE]);
+		sp.fEx[k] = e[6 * FAR_FACE]; sp.fEy[k] = e[7 * FAR_FACE];
+	}
 }
 
 /* Moves every block's particles (own segment, then pending arrivals) into a species laid

@@ -393,8 +393,9 @@ alloc_species(sim_t_ *s, int is, int cap)
 	}
 	h.arr = 0;
 
-	CK(cudaMalloc(&h.fblock, (size_t) FAR_CAP * 10 * sizeof(double) + 256));
-	CK(cudaMemsetAsync(h.fblock, 0, (size_t) FAR_CAP * 10 * sizeof(double) + 256, s->stream));
+	const size_t fbytes = ((size_t) FAR_CAP * 10 + (size_t) FAR_FACE * 16) * sizeof(double) + 256;
+	CK(cudaMalloc(&h.fblock, fbytes));
+	CK(cudaMemsetAsync(h.fblock, 0, fbytes, s->stream));
 	{
 		double *f = (double *) h.fblock;
 		h.d.fx = f; h.d.fy = f + FAR_CAP; h.d.fux = f + 2 * FAR_CAP; h.d.fuy = f + 3 * FAR_CAP;
@@ -402,7 +403,10 @@ alloc_species(sim_t_ *s, int is, int cap)
 		h.d.fid = (long long *) (f + 7 * FAR_CAP);
 		h.d.fkey = (long long *) (f + 8 * FAR_CAP);
 		h.d.fidx = (int *) (f + 9 * FAR_CAP);
-		h.d.fcount = (int *) (f + 10 * FAR_CAP);
+		h.d.rfar[0] = f + 10 * FAR_CAP;
+		h.d.rfar[1] = f + 10 * FAR_CAP + 8 * FAR_FACE;
+		h.d.fcount = (int *) (f + 10 * FAR_CAP + 16 * FAR_FACE);
+		h.d.rfcount = h.d.fcount + 4;
 	}
 
 	if(s->p.keep_particle_E) return ensure_particle_E(s, is);
@@ -883,7 +887,17 @@ exchange(sim_t_ *s)
 		sps[nsp] = &h.d;
 		arrs[nsp++] = h.arr;
 	}
-	if(s->comm && nsp) return comm_particles(s->comm, sps, arrs, nsp, s->g, s->nb, s->stream, s->errflag, &s->launches);
+	if(s->comm && nsp)
+	{
+		int rc = comm_particles(s->comm, sps, arrs, nsp, s->g, s->nb, s->stream, s->errflag, &s->launches);
+		if(rc) return rc;
+		/* far movers received from the neighbour ranks */
+		for(int i = 0; i < nsp; i++)
+		{
+			k_far_insert<<<1, 1024, 0, s->stream>>>(*sps[i], s->g, s->errflag);
+			if((rc = check_launch(s))) return rc;
+		}
+	}
 	return 0;
 }
 

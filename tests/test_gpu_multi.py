@@ -27,7 +27,7 @@ def run_ranks(n, conf, steps, mode="fused", port=29611):
 
 
 @pytest.mark.parametrize("conf,mode", [("uniform-small.conf", "fused"), ("2d-2species-small.conf", "staged"),
-                                       ("two-streams.conf", "fused")])
+                                       ("two-streams.conf", "fused"), ("far-beam.conf", "fused")])
 def test_two_ranks(conf, mode):
     if ngpus() < 2:
         pytest.skip("needs 2 GPUs")

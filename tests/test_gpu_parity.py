@@ -12,7 +12,7 @@ from cpic_b200 import Sim, Params, load_conf, init_particles
 pytestmark = pytest.mark.gpu
 
 CONFS = ["uniform-small.conf", "2d-2species-small.conf", "2d-2species-delta.conf", "two-streams.conf",
-         "harmonic-64.conf", "cyclotron.conf"]
+         "harmonic-64.conf", "cyclotron.conf", "far-beam.conf"]
 
 
 @pytest.mark.parametrize("shape", [(64, 64), (128, 32), (4, 4), (8, 16), (256, 128)])
