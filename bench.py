@@ -45,7 +45,7 @@ def ncu_traffic(kernel="k_gather_push<2>", path=None):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the
     committed `ncu --set full` extract of the same workload (profiles/, config A, one GPU)."""
     import csv
-    path = path or os.path.join(ROOT, "profiles", "r1e_ncu_full_summary.csv")
+    path = path or os.path.join(ROOT, "profiles", "r1f_ncu_full_summary.csv")
     try:
         rows = list(csv.reader(open(path)))
         hdr = rows[0]
@@ -332,7 +332,7 @@ def main():
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": peak_src,
                 "traffic": ncu_traffic() if (world == 1 and args.workload == "A") else None,
-                "traffic_source": "profiles/r1e_ncu_full_summary.csv (bytes per launch, mean of the two species)",
+                "traffic_source": "profiles/r1f_ncu_full_summary.csv (bytes per launch, mean of the two species)",
                 "algorithmic_bytes_per_particle": BYTES_GATHER_PUSH, "particles_per_launch": nps,
                 "avg_launch_ms": t_push,
                 "whole_step_frac": (n_rank * args.steps / (ms * 1e-3)) * (BYTES_GATHER_PUSH + BYTES_DEPOSIT) / 1e9 / peak,
