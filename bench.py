@@ -232,6 +232,10 @@ def main():
     params.Ly = params.Ly * (ny / 1024) * world
     # keep the physics of the conf: e0 scales with the particle density (plasma frequency fixed)
     params.e0 = params.e0 * (nps / 5_000_000) / ((nx / 1024) * (ny / 1024))
+    if world > 1:
+        # capacities cannot grow on the fly with several ranks (they must stay equal): more slack up front
+        params.capacity_factor = 2.0
+        params.outbox_fraction = 0.4
     nspecies = len(params.q)
     n_rank = nps * nspecies
     n_total = n_rank * world

@@ -14,7 +14,8 @@ class Cpic_b200Error(RuntimeError):
 
 
 def lib_path():
-    return os.path.join(_HERE, "libcpic_b200.so")
+    # CPIC_B200_LIB: an alternative build of the same library (kernel tuning experiments)
+    return os.environ.get("CPIC_B200_LIB") or os.path.join(_HERE, "libcpic_b200.so")
 
 
 def build(force=False):

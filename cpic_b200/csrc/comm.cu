@@ -30,6 +30,7 @@ typedef struct ncclComm *ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 typedef int ncclResult_t;
 enum { ncclInt8 = 0, ncclInt32 = 2, ncclInt64 = 4, ncclFloat64 = 8 };
+enum { ncclSum = 0, ncclProd = 1, ncclMax = 2, ncclMin = 3 };
 
 struct Nccl {
 	void *lib;
@@ -38,6 +39,7 @@ struct Nccl {
 	ncclResult_t (*CommDestroy)(ncclComm_t);
 	ncclResult_t (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t);
 	ncclResult_t (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t);
+	ncclResult_t (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t);
 	ncclResult_t (*GroupStart)(void);
 	ncclResult_t (*GroupEnd)(void);
 	const char *(*GetErrorString)(ncclResult_t);
@@ -69,6 +71,7 @@ load_nccl(char *err, size_t errlen)
 	SYM(CommDestroy, "ncclCommDestroy");
 	SYM(Send, "ncclSend");
 	SYM(Recv, "ncclRecv");
+	SYM(AllReduce, "ncclAllReduce");
 	SYM(GroupStart, "ncclGroupStart");
 	SYM(GroupEnd, "ncclGroupEnd");
 	SYM(GetErrorString, "ncclGetErrorString");
@@ -196,6 +199,15 @@ comm_destroy(Comm *c)
 	cudaFree(c->rho_recv); cudaFree(c->a); cudaFree(c->sb); cudaFree(c->tb); cudaFree(c->GT);
 	if(c->nc) g_nccl.CommDestroy(c->nc);
 	delete c;
+}
+
+/* Element-wise maximum of a few ints over the ranks, in place (error words, capacity
+ * requests): what MPI_Bcast(&sim->running) is to the reference (src/sim.c:578) */
+int
+comm_allreduce_max(Comm *c, int *dev, int n, cudaStream_t stream)
+{
+	NCK(g_nccl.AllReduce(dev, dev, (size_t) n, ncclInt32, ncclMax, c->nc, stream));
+	return 0;
 }
 
 /* comm_send_ghost_rho + comm_recv_ghost_rho, reference src/comm_field.c:51-136 */

@@ -18,6 +18,9 @@ Comm *comm_create(const void *id128, int rank, int nranks, const Geom &g, cudaSt
 		char *err, size_t errlen);
 void comm_destroy(Comm *c);
 
+/* element-wise maximum of n ints over the ranks, in place */
+int comm_allreduce_max(Comm *c, int *dev, int n, cudaStream_t stream);
+
 /* rho: ghost row ny -> rank+1, received row added to row 0 */
 int comm_rho_halo(Comm *c, double *rho, cudaStream_t stream, long long *launches);
 /* phi: slab rows 0,1 -> rank-1's south ghosts; slab row ny-1 -> rank+1's north ghost */

@@ -22,7 +22,9 @@
 #include "geom.h"
 
 #define FULL 0xffffffffu
+#ifndef MAX_WPC
 #define MAX_WPC 8
+#endif
 
 /* Outbox: the particles that left their block in one push, one region per block and
  * destination code (geom.h), so that the receiving block finds its arrivals as
@@ -394,14 +396,20 @@ arrival_slot(const Arrivals &A, const SpeciesDev &sp, int f)
  * position); one that leaves goes to the region of its destination in outbox `cur`.
  * Ranks inside a batch come from ballots, so the order is: batches in order, lanes in
  * order. MODE 0 moves nothing. */
+#ifndef PIPE_STAGES
 #define PIPE_STAGES 3
+#endif
 #define PUSH_SMEM_HEADER 384      /* tile barrier + MAX_WPC * PIPE_STAGES stage barriers */
 
 /* arrays staged per batch: x y (ux uy uz id) (Ex Ey) */
 template <int MODE> struct PipeArrays { static const int N = MODE == 0 ? 2 : MODE == 2 ? 6 : 8; };
 
+#ifndef PUSH_MIN_CTAS
+#define PUSH_MIN_CTAS 4
+#endif
+
 template <int MODE>
-__global__ void __launch_bounds__(32 * MAX_WPC, 4)
+__global__ void __launch_bounds__(32 * MAX_WPC, PUSH_MIN_CTAS)
 k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 		const __grid_constant__ CUtensorMap mapEx, const __grid_constant__ CUtensorMap mapEy,
 		int nb, int cur, int *__restrict__ errflag)

@@ -246,9 +246,10 @@ cpic_b200_create(const cpic_b200_params_t *pp, cpic_b200_sim_t **out)
 	CKD(cudaMalloc(&s->hr, (size_t) ncx * g.ny * sizeof(double)));
 	CKD(cudaMalloc(&s->hc, (size_t) g.nby * ncx * sizeof(double)));
 	CKD(cudaMalloc(&s->red, ((size_t) std::max(s->nb, g.ny) + 16) * sizeof(double)));
-	CKD(cudaMalloc(&s->errflag, sizeof(int)));
-	CKD(cudaMemset(s->errflag, 0, sizeof(int)));
-	CKD(cudaMallocHost(&s->h_err, sizeof(int)));
+	/* [0] deferred error bits, [1 .. MAX_SPECIES] capacity requests (agreed over the ranks) */
+	CKD(cudaMalloc(&s->errflag, 16 * sizeof(int)));
+	CKD(cudaMemset(s->errflag, 0, 16 * sizeof(int)));
+	CKD(cudaMallocHost(&s->h_err, 16 * sizeof(int)));
 
 	if(p.nranks == 1)
 	{
@@ -597,7 +598,8 @@ regrow(sim_t_ *s, int is, int newcap)
 static int
 check_capacity(sim_t_ *s)
 {
-	if(s->comm) return 0;
+	int want[CPIC_B200_MAX_SPECIES] = { 0 };
+	bool any = false;
 	for(int is = 0; is < s->p.nspecies; is++)
 	{
 		int64_t o[6];
@@ -606,13 +608,32 @@ check_capacity(sim_t_ *s)
 		if(!o[1]) continue;
 		const bool tight = o[0] * 10 > o[1] * 8 || o[2] * 10 > o[3] * 8 || o[4] * 10 > o[5] * 8;
 		if(!tight) continue;
-		int64_t want = std::max<int64_t>(o[1] * 3 / 2, o[0] * 2);
+		int64_t w = std::max<int64_t>(o[1] * 3 / 2, o[0] * 2);
 		/* regions scale with the block capacity; make sure they clear the observed peaks */
 		const double frac = s->p.outbox_fraction > 0 ? s->p.outbox_fraction : 0.3;
-		want = std::max<int64_t>(want, (int64_t) (2.0 * o[2] / frac));
-		want = std::max<int64_t>(want, (int64_t) (8.0 * o[4] / frac));
-		want = (want + 31) / 32 * 32;
-		rc = regrow(s, is, (int) std::min<int64_t>(want, 1 << 30));
+		w = std::max<int64_t>(w, (int64_t) (2.0 * o[2] / frac));
+		w = std::max<int64_t>(w, (int64_t) (8.0 * o[4] / frac));
+		w = (w + 31) / 32 * 32;
+		want[is] = (int) std::min<int64_t>(w, 1 << 30);
+		any = true;
+	}
+	if(s->comm)
+	{
+		/* every rank must keep the same capacities (the exchange buffers are sized from them):
+		 * the largest request wins. All ranks reach this point at the same steps. */
+		for(int is = 0; is < s->p.nspecies; is++) s->h_err[1 + is] = want[is];
+		CK(cudaMemcpyAsync(s->errflag + 1, s->h_err + 1, (size_t) s->p.nspecies * sizeof(int), cudaMemcpyHostToDevice, s->stream));
+		if(comm_allreduce_max(s->comm, s->errflag + 1, s->p.nspecies, s->stream)) return CPIC_B200_ECUDA;
+		CK(cudaMemcpyAsync(s->h_err + 1, s->errflag + 1, (size_t) s->p.nspecies * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+		CK(cudaStreamSynchronize(s->stream));
+		any = false;
+		for(int is = 0; is < s->p.nspecies; is++) { want[is] = s->h_err[1 + is]; any = any || want[is] > 0; }
+	}
+	if(!any) return 0;
+	for(int is = 0; is < s->p.nspecies; is++)
+	{
+		if(want[is] <= 0 || !s->sp[is].block || want[is] <= s->sp[is].d.cap) continue;
+		int rc = regrow(s, is, want[is]);
 		if(rc) return rc;
 	}
 	return 0;
@@ -1065,6 +1086,8 @@ cpic_b200_sync(cpic_b200_sim_t *s)
 {
 	if(!s) return fail(CPIC_B200_EINVAL, "null sim");
 	CK(cudaSetDevice(s->device));
+	/* with several ranks an error anywhere is an error everywhere (no rank is left waiting) */
+	if(s->comm && comm_allreduce_max(s->comm, s->errflag, 1, s->stream)) return CPIC_B200_ECUDA;
 	CK(cudaMemcpyAsync(s->h_err, s->errflag, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
 	CK(cudaStreamSynchronize(s->stream));
 	const int e = *s->h_err;

@@ -25,6 +25,8 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     params, run = load_conf(conf, rank=rank, nranks=world, device=local)
+    if os.environ.get("MGPU_TIGHT"):
+        params.capacity_factor = 1.01        # forces the collective capacity growth (check_capacity)
     parts = init_particles(conf)
     o = oracle_from(params, parts)
     g = Sim(params)
@@ -72,7 +74,14 @@ def main():
         check(f"iteration {it}")
     t = torch.tensor([max(worst.values())], device="cuda", dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    caps = [g.capacity(i) for i in range(len(params.q))]
+    ct = torch.tensor(caps, device="cuda", dtype=torch.int64)
+    cmax, cmin = ct.clone(), ct.clone()
+    dist.all_reduce(cmax, op=dist.ReduceOp.MAX)
+    dist.all_reduce(cmin, op=dist.ReduceOp.MIN)
+    assert torch.equal(cmax, cmin), f"block capacities differ between ranks: {caps}"
     if rank == 0:
+        print(f"MGPU-CAPS {caps}")
         print(f"MGPU-OK world={world} conf={os.path.basename(conf)} steps={steps} worst={t.item():.2e}")
     g.close()
     dist.destroy_process_group()

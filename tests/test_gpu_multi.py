@@ -18,12 +18,13 @@ def ngpus():
         return 0
 
 
-def run_ranks(n, conf, steps, mode="fused", port=29611):
+def run_ranks(n, conf, steps, mode="fused", port=29611, env=None):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
            "--master-addr", "127.0.0.1", "--master-port", str(port),
            os.path.join(ROOT, "tests", "mgpu_worker.py"), conf_path(conf), str(steps), mode]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, **(env or {})))
     assert r.returncode == 0 and "MGPU-OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+    return r.stdout
 
 
 @pytest.mark.parametrize("conf,mode", [("uniform-small.conf", "fused"), ("2d-2species-small.conf", "staged"),
@@ -38,3 +39,12 @@ def test_four_ranks():
     if ngpus() < 4:
         pytest.skip("needs 4 GPUs")
     run_ranks(4, "uniform-small.conf", 10, "fused", port=29613)
+
+
+def test_two_ranks_capacity_growth():
+    """Tight block capacities: the ranks must agree on a larger capacity on the fly
+    (check_capacity over NCCL) and stay identical to the oracle."""
+    if ngpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    out = run_ranks(2, "uniform-small.conf", 40, "fused", port=29615, env={"MGPU_TIGHT": "1"})
+    assert "MGPU-CAPS" in out
