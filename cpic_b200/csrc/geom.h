@@ -62,26 +62,12 @@ struct Geom {
 	double y0;           /* slab origin: field.x0[Y] = rank * ny * dy (src/field.c:149-151) */
 };
 
-/* Cell of a position, the reference's way (src/interpolate.c:38-66: block_delta * idx,
- * floor), clamped into the slab so that a particle sitting exactly on the upper edge
- * (x == L after a wrap from -eps, src/comm_plasma.c:738-742) stays addressable.
- * Returns the clamped floor as a double (needed for the in-cell offset). */
-HD double
-cell_floor_x(const Geom &g, double x)
-{
-	double bs = floor(MUL(x, g.idx));
-	return fmin(fmax(bs, 0.0), (double) (g.nx - 1));
-}
-
-HD double
-cell_floor_y(const Geom &g, double y)
-{
-	double bs = floor(MUL(SUB(y, g.y0), g.idy));
-	return fmin(fmax(bs, 0.0), (double) (g.ny - 1));
-}
-
-/* Integer forms: floor through one round-down conversion, clamped in integer registers.
- * Same cells as the double forms above for every position inside the domain. */
+/* Cell of a position, the reference's way (src/interpolate.c:38-66: floor(x * idx), one
+ * round-down conversion here), clamped into the domain so that a particle sitting exactly
+ * on the upper edge (x == L after a wrap from -eps, src/comm_plasma.c:738-742) stays
+ * addressable. Rows are always formed from the GLOBAL coordinate (floor(y * idy)) and then
+ * made slab-relative as integers: every kernel and the host binning agree on the cell of a
+ * particle whatever the rank, and the arithmetic is that of the single-rank reference. */
 HD int
 cell_ix(const Geom &g, double x)
 {
@@ -93,18 +79,7 @@ cell_ix(const Geom &g, double x)
 	return c < 0 ? 0 : (c > g.nx - 1 ? g.nx - 1 : c);
 }
 
-HD int
-cell_iy(const Geom &g, double y)
-{
-#ifdef __CUDA_ARCH__
-	int c = __double2int_rd(MUL(SUB(y, g.y0), g.idy));
-#else
-	int c = (int) floor((y - g.y0) * g.idy);
-#endif
-	return c < 0 ? 0 : (c > g.ny - 1 ? g.ny - 1 : c);
-}
-
-/* Global row of a position (for the exchange between slabs) */
+/* Global row of a position */
 HD int
 global_row(const Geom &g, double y)
 {
@@ -116,9 +91,17 @@ global_row(const Geom &g, double y)
 	return c < 0 ? 0 : (c > g.ny_glob - 1 ? g.ny_glob - 1 : c);
 }
 
+/* Row inside this rank's slab */
+HD int
+cell_iy(const Geom &g, double y)
+{
+	int c = global_row(g, y) - g.row0;
+	return c < 0 ? 0 : (c > g.ny - 1 ? g.ny - 1 : c);
+}
+
 /* Bilinear (CIC) weights, restating reference src/interpolate.c:77-100 (weights),
  * :38-66 (relative_position_grid) and :11-32 (linear_interpolation). The Y offset uses
- * dx[X] as the reference does (src/interpolate.c:87-88). */
+ * dx[X] as the reference does (src/interpolate.c:87-88). i0y is slab-relative. */
 HD void
 cic_weights(const Geom &g, double x, double y, int &i0x, int &i0y,
 		double &w00, double &w01, double &w10, double &w11)
@@ -130,9 +113,10 @@ cic_weights(const Geom &g, double x, double y, int &i0x, int &i0y,
 	bs = (double) i0x;
 	relx = MUL(SUB(bd, MUL(bs, g.dx)), g.idx);
 
-	bd = SUB(y, g.y0);
+	/* global row and global offset: (y - row*dx) is what the single-rank reference forms */
+	bd = y;
 	i0y = cell_iy(g, y);
-	bs = (double) i0y;
+	bs = (double) (i0y + g.row0);
 	rely = MUL(SUB(bd, MUL(bs, g.dx)), g.idy);
 
 	delx = SUB(1.0, relx);
