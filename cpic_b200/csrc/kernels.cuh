@@ -23,14 +23,16 @@
 
 #define FULL 0xffffffffu
 
-/* Layout switches (both on by default; 0 keeps the plain layouts for A/B measurements):
+/* Layout switches, off by default. Both were measured on B200 (config A, round 1) and change
+ * nothing (E_INTERLEAVED: 0.2984 vs 0.2987 ms per step in the push kernels) or lose slightly
+ * (DEP_RECORDS: 0.165 vs 0.157 ms in the deposit); they stay for the next round's profiling.
  * E_INTERLEAVED: the gather reads (E_x, E_y) pairs from one interleaved tile with 16-byte loads
  * DEP_RECORDS:   the deposit keeps the four corner sums of a cell in one 32-byte record */
 #ifndef E_INTERLEAVED
-#define E_INTERLEAVED 1
+#define E_INTERLEAVED 0
 #endif
 #ifndef DEP_RECORDS
-#define DEP_RECORDS 1
+#define DEP_RECORDS 0
 #endif
 #ifndef MAX_WPC
 #define MAX_WPC 8
