@@ -33,6 +33,8 @@ WORKLOADS = {
     "A": ("2d-2species.conf", 1024, 1024, 5_000_000),
     "B": ("2d-2species.conf", 2048, 2048, 50_000_000),
     "C": ("2d-2species.conf", 4096, 4096, 500_000_000),
+    # BASELINE configs[2]: cyclotron physics at scale (one species, uniform B, 2048^2, 1e8 particles)
+    "cyc": ("cyclotron-2048.conf", 2048, 2048, 100_000_000),
 }
 
 
@@ -143,6 +145,10 @@ def cpu_reference(conf, steps, warmup, budget_s=150.0):
     sample_conf = conf if per_species == run.nparticles[0] else scaled_conf(conf, per_species)
     n = per_species * len(run.nparticles)
     from _refbind import RefSim, ref_available
+    # the reference prints to stdout (print_affinity, src/solver.c:190-205): keep stdout for the one JSON line
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if ref_available("ref"):
         kind = "reference"
         sim = RefSim(sample_conf, "ref")
@@ -160,6 +166,8 @@ def cpu_reference(conf, steps, warmup, budget_s=150.0):
     for _ in range(steps):
         step()
     dt = time.perf_counter() - t0
+    os.dup2(saved_stdout, 1)
+    os.close(saved_stdout)
     value = n * steps / dt
     info = {"value": value, "unit": UNIT, "cores": 1, "kind": kind,
             "sample": f"{os.path.basename(conf)}: {params.nx}x{params.ny} grid, {n} particles "
@@ -178,10 +186,12 @@ def run_reference(args):
     steps = min(args.steps, 20)
     warmup = min(args.warmup, 2)
     value, info = cpu_reference(conf, steps, warmup)
+    from cpic_b200 import load_conf
+    nsp = len(load_conf(conf)[1].nparticles)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": info["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{name} ({nx}x{ny}, {2 * nps} particles)", "host": "CPU, 1 core"},
+            "config": {"workload": f"{name} ({nx}x{ny}, {nsp * nps} particles)", "host": "CPU, 1 core"},
             "cpu_baseline": {k: info[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -226,12 +236,15 @@ def main():
         ny, nps = ny // world, nps // world          # per GPU: a slab of the fixed global problem
     conf = os.path.join(ROOT, "conf", name)
     params, run = load_conf(conf, rank=rank, nranks=world, device=local)
-    params.nx, params.ny = nx, ny * world        # weak scaling: one nx x ny slab per GPU
-    # the cell size of the conf is kept (dx = 4/1024) whatever the grid: same cells-per-step physics
-    params.Lx = params.Lx * (nx / 1024)
-    params.Ly = params.Ly * (ny / 1024) * world
-    # keep the physics of the conf: e0 scales with the particle density (plasma frequency fixed)
-    params.e0 = params.e0 * (nps / 5_000_000) / ((nx / 1024) * (ny / 1024))
+    if args.workload == "cyc":
+        params.ny, params.Ly = ny * world, params.Ly * world
+    else:
+        params.nx, params.ny = nx, ny * world        # weak scaling: one nx x ny slab per GPU
+        # the cell size of the conf is kept (dx = 4/1024) whatever the grid: same cells-per-step physics
+        params.Lx = params.Lx * (nx / 1024)
+        params.Ly = params.Ly * (ny / 1024) * world
+        # keep the physics of the conf: e0 scales with the particle density (plasma frequency fixed)
+        params.e0 = params.e0 * (nps / 5_000_000) / ((nx / 1024) * (ny / 1024))
     if world > 1:
         # capacities cannot grow on the fly with several ranks (they must stay equal): more slack up front
         params.capacity_factor = 2.0
@@ -249,7 +262,7 @@ def main():
         data = "synthetic (reference initialiser: uniform random positions, u~U(-v,v), seed 138)"
     else:
         vs = float(os.environ.get("BENCH_VSCALE", "1.0"))     # experiments: colder / hotter plasma
-        drift = [(5.0 * vs, 0.0), (3.0 * vs, 0.0)]
+        drift = [(5.0 * vs, 0.0), (3.0 * vs, 0.0)] if args.workload != "cyc" else [(10.0 * vs, 10.0 * vs)]
         for i in range(nspecies):
             sim.init_uniform(i, nps, id0=rank * nps, vx=drift[i][0], vy=drift[i][1], seed=138 + i)
         data = "synthetic (device initialiser: uniform positions per particle block, u~U(-v,v))"
@@ -400,8 +413,8 @@ def main():
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f64", "data": data,
                 "config": {"workload": f"{name}: {nx}x{ny} grid and {n_rank} particles per GPU "
-                                       f"({params.nx}x{params.ny}, {n_total} particles in total), 2 species, "
-                                       f"B=(0,0,-0.2), dt=5e-3",
+                                       f"({params.nx}x{params.ny}, {n_total} particles in total), {nspecies} species, "
+                                       f"B=({params.B[0]:g},{params.B[1]:g},{params.B[2]:g}), dt={params.dt:g}",
                            "parallelism": f"{world} Y-slab(s), one per GPU",
                            "l2": "particle state per GPU (%.0f MB) exceeds the 126 MB L2" % (n_rank * 48 / 1e6)},
                 "clocks": clk, "e2e": e2e, "gpu_launches": int(launches0),
