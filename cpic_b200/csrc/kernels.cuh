@@ -583,6 +583,9 @@ k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 		const int t = (own ? bi : bi - nbo) * 32 + lane; /* index inside the segment / the arrivals */
 		const bool valid = t < (own ? cnt : A.total);
 
+		/* the stage refilled below was read in the previous iteration: MODE 0 has no ballot in
+		 * between that would order those reads before lane 0's refill */
+		if(MODE == 0) __syncwarp();
 		/* keep the pipeline full: batch bi + PIPE_STAGES - 1. The ids are needed only by
 		 * particles that change slot: every arrival, and segment particles once the write
 		 * cursor lags the read position (a late fetch covers the batch where that starts). */

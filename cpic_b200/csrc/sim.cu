@@ -244,6 +244,8 @@ cpic_b200_create(const cpic_b200_params_t *pp, cpic_b200_sim_t **out)
 	CKD(cudaMalloc(&s->Ey, (size_t) (g.ny + 1) * g.SE * sizeof(double)));
 	CKD(cudaMemset(s->rho, 0, (size_t) (g.ny + 1) * g.S * sizeof(double)));
 	CKD(cudaMemset(s->phi, 0, (size_t) (g.ny + 3) * g.S * sizeof(double)));
+	/* cuFFT leaves the padding columns [nx, S) of its real output alone; they are copied into phi */
+	CKD(cudaMemset(s->phi_raw, 0, (size_t) g.ny * g.S * sizeof(double)));
 	CKD(cudaMemset(s->Ex, 0, (size_t) (g.ny + 1) * g.SE * sizeof(double)));
 	CKD(cudaMemset(s->Ey, 0, (size_t) (g.ny + 1) * g.SE * sizeof(double)));
 	CKD(cudaMalloc(&s->Exy, (size_t) (g.ny + 1) * g.SE * sizeof(double2)));

@@ -20,8 +20,14 @@ def _have_gpu():
         return False
 
 
+def _simt_check():
+    """True inside the subprocess that tests/test_simt_check.py starts: the gpu-marked parity tests then
+    run against the kernels interpreted on the CPU (tests/simt), which needs no device."""
+    return os.environ.get("CPIC_B200_SIMT_CHECK") == "1" and "simt" in os.environ.get("CPIC_B200_LIB", "")
+
+
 def pytest_collection_modifyitems(config, items):
-    if _have_gpu():
+    if _have_gpu() or _simt_check():
         return
     skip = pytest.mark.skip(reason="no CUDA device")
     for item in items:

@@ -500,6 +500,18 @@ launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> &fn)
 
 }  /* namespace simt */
 
+/* Clears a reported fault (deadlock, misuse of a primitive) so that the next launch runs */
+extern "C" void
+simt_check_reset(void)
+{
+	simt::aborting = false;
+	simt::last_error = cudaSuccess;
+	simt::abort_msg[0] = 0;
+}
+
+extern "C" long long simt_check_launches(void) { return simt::n_launches; }
+extern "C" long long simt_check_switches(void) { return simt::n_switches; }
+
 /* ------------------------------------------------------------ runtime API */
 
 cudaError_t

@@ -1,0 +1,72 @@
+"""The device code on the CPU: cpic_b200/csrc/{kernels.cuh,sim.cu,comm.cu} compiled with g++
+against the lockstep SIMT interpreter of tests/simt (fibers per CUDA thread, warp collectives
+that wait for their participants, asynchronous copies that land at their wait, poisoned fresh
+memory), then the gpu-marked parity tests run against that build in a subprocess.
+
+This is test infrastructure: the package never builds or loads tests/simt, and a parity claim
+is only ever made by the `-m gpu` run on the B200. What it buys on a box without a GPU is a
+check of the kernels' logic -- indices, compaction order, capacities, barrier protocols,
+races between lanes that hardware lockstep hides (it found two in round 1) -- against the
+same oracle and the same assertions as the GPU run."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+SIMT = os.path.join(ROOT, "tests", "simt")
+LIB = os.path.join(SIMT, "_build", "libcpic_b200_simt.so")
+
+
+@pytest.fixture(scope="module")
+def simt_build():
+    r = subprocess.run(["make", "-C", SIMT], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert os.path.exists(LIB)
+    return LIB
+
+
+def run_under_interpreter(lib, args, timeout=900):
+    env = dict(os.environ, CPIC_B200_LIB=lib, CPIC_B200_SIMT_CHECK="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-p", "no:cacheprovider", "-m", "gpu"] + args,
+                       cwd=ROOT, env=env, capture_output=True, text=True, timeout=timeout)
+    tail = (r.stdout + r.stderr)[-4000:]
+    assert r.returncode == 0, tail
+    assert " passed" in r.stdout and "failed" not in r.stdout and "skipped" not in r.stdout, tail
+    return r.stdout
+
+
+def test_interpreter_selftest(simt_build):
+    """Collectives, CTA barriers, late-landing cp.async / TMA copies, zero fill of tensor tiles,
+    the driver's tensor-map checks and the deadlock report, each against a known answer."""
+    r = subprocess.run([os.path.join(SIMT, "_build", "selftest")], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "selftest: ok" in r.stdout
+
+
+def test_product_library_is_not_the_interpreter():
+    """The shipped library must not contain the interpreter, and the package must not look for it."""
+    import cpic_b200._lib as L
+    path = L.lib_path() if "CPIC_B200_LIB" not in os.environ else os.path.join(ROOT, "cpic_b200", "libcpic_b200.so")
+    assert "simt" not in os.path.basename(path)
+    out = subprocess.run(["nm", "-D", "--defined-only", path], capture_output=True, text=True).stdout
+    assert "simt_check_reset" not in out and "simt_switch" not in out
+    for name in os.listdir(os.path.join(ROOT, "cpic_b200")):
+        if name.endswith(".py"):
+            assert "simt" not in open(os.path.join(ROOT, "cpic_b200", name)).read(), name
+
+
+def test_kernel_parity_suite_under_the_interpreter(simt_build):
+    """tests/test_gpu_parity.py, every case: solver, stage_field_E, deposit, the first 10 steps of
+    seven configurations staged and fused, bitwise fused == staged, determinism, hot beam, velocity
+    limit, ragged species, far movers, image round trip -- same oracle, same 1e-12."""
+    out = run_under_interpreter(simt_build, ["tests/test_gpu_parity.py"])
+    assert "36 passed" in out or int(out.strip().splitlines()[-1].split()[0]) >= 36, out[-500:]
+
+
+def test_physics_under_the_interpreter(simt_build):
+    """Two-stream growth rate and energy history, constant speed and cyclotron orbits (the 1200-step
+    harmonic golden trajectory is left to the GPU run: minutes of interpretation)."""
+    run_under_interpreter(simt_build, ["tests/test_gpu_physics.py", "-k", "two_stream or constant_speed or cyclotron"])
