@@ -22,16 +22,22 @@ def main():
     conf, steps = sys.argv[1], int(sys.argv[2])
     fused = len(sys.argv) < 4 or sys.argv[3] == "fused"
     rank, world, local = env_rank()
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    # MGPU_DEVICE=cpu: the ranks are CPU processes running the kernels under tests/simt (gloo carries
+    # the id, tests/simt/fake_nccl.c the library's traffic); default: one GPU per rank over NCCL
+    dev = os.environ.get("MGPU_DEVICE", "cuda")
+    if dev == "cuda":
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        dist.init_process_group("gloo")
     params, run = load_conf(conf, rank=rank, nranks=world, device=local)
     if os.environ.get("MGPU_TIGHT"):
         params.capacity_factor = 1.01        # forces the collective capacity growth (check_capacity)
     parts = init_particles(conf)
     o = oracle_from(params, parts)
     g = Sim(params)
-    set_particles_collective(g, partition(parts, params, rank), dist, device="cuda")
-    bootstrap(g, dist, device="cuda")
+    set_particles_collective(g, partition(parts, params, rank), dist, device=dev)
+    bootstrap(g, dist, device=dev)
     o.pre_step()
     g.pre_step()
     nyl = params.ny // world
@@ -72,10 +78,10 @@ def main():
             g.step_staged()
         o.step()
         check(f"iteration {it}")
-    t = torch.tensor([max(worst.values())], device="cuda", dtype=torch.float64)
+    t = torch.tensor([max(worst.values())], device=dev, dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     caps = [g.capacity(i) for i in range(len(params.q))]
-    ct = torch.tensor(caps, device="cuda", dtype=torch.int64)
+    ct = torch.tensor(caps, device=dev, dtype=torch.int64)
     cmax, cmin = ct.clone(), ct.clone()
     dist.all_reduce(cmax, op=dist.ReduceOp.MAX)
     dist.all_reduce(cmin, op=dist.ReduceOp.MIN)

@@ -538,9 +538,11 @@ cudaMemcpy2DAsync(void *d, size_t dpitch, const void *s, size_t spitch, size_t w
 
 cudaError_t cudaMemset(void *d, int v, size_t n) { memset(d, v, n); return cudaSuccess; }
 cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t) { memset(d, v, n); return cudaSuccess; }
-cudaError_t cudaSetDevice(int d) { return d == 0 ? cudaSuccess : cudaErrorInvalidValue; }
-cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
-cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
+/* every rank of a multi-process test names its own "device" */
+static int cur_device;
+cudaError_t cudaSetDevice(int d) { if(d < 0 || d >= 16) return cudaErrorInvalidValue; cur_device = d; return cudaSuccess; }
+cudaError_t cudaGetDevice(int *d) { *d = cur_device; return cudaSuccess; }
+cudaError_t cudaGetDeviceCount(int *n) { *n = 16; return cudaSuccess; }
 
 cudaError_t
 cudaGetLastError(void)

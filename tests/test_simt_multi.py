@@ -1,0 +1,59 @@
+"""Several ranks on the CPU: the multi-GPU path of the library (Y slabs, particle faces with
+far movers, rho/phi ghost rows, distributed FFT, capacity agreement; cpic_b200/csrc/comm.cu)
+with the kernels run by the SIMT interpreter of tests/simt and NCCL replaced by
+tests/simt/fake_nccl.c (files between processes). Same worker and same assertions against the
+single-rank oracle as tests/test_gpu_multi.py runs on real GPUs; torch.distributed (gloo)
+only carries the 128-byte id. Test infrastructure only -- see tests/test_simt_check.py."""
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+
+from conftest import conf_path, ROOT
+from test_simt_check import simt_build, SIMT  # noqa: F401  (fixture)
+
+
+def free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def run_ranks_cpu(lib, n, conf, steps, mode="fused", env=None, timeout=600):
+    base = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(free_port()), WORLD_SIZE=str(n),
+                MGPU_DEVICE="cpu", CPIC_B200_LIB=lib, CPIC_B200_SIMT_CHECK="1",
+                CPIC_B200_NCCL=os.path.join(SIMT, "_build", "libfake_nccl.so"), **(env or {}))
+    procs = []
+    for r in range(n):
+        e = dict(base, RANK=str(r), LOCAL_RANK=str(r))
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "mgpu_worker.py"),
+                                       conf_path(conf), str(steps), mode], env=e, cwd=ROOT,
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = []
+    try:
+        for p in procs:
+            outs.append(p.communicate(timeout=timeout)[0])
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
+    bad = [i for i, p in enumerate(procs) if p.returncode != 0]
+    assert not bad and "MGPU-OK" in outs[0], "\n".join(f"--- rank {i}\n{o[-2500:]}" for i, o in enumerate(outs))
+    return outs[0]
+
+
+@pytest.mark.parametrize("conf,mode", [("uniform-small.conf", "fused"), ("2d-2species-small.conf", "staged"),
+                                       ("two-streams.conf", "fused"), ("far-beam.conf", "fused")])
+def test_two_ranks_on_cpu(simt_build, conf, mode):
+    run_ranks_cpu(simt_build, 2, conf, 10, mode)
+
+
+def test_four_ranks_on_cpu(simt_build):
+    run_ranks_cpu(simt_build, 4, "uniform-small.conf", 10)
+
+
+def test_capacity_growth_is_agreed_between_ranks_on_cpu(simt_build):
+    out = run_ranks_cpu(simt_build, 2, "uniform-small.conf", 40, env={"MGPU_TIGHT": "1"})
+    assert "MGPU-CAPS" in out
