@@ -37,6 +37,12 @@
 #ifndef MAX_WPC
 #define MAX_WPC 8
 #endif
+/* OWN_BULK 1: a batch of the own segment is fetched by one lane with one TMA bulk copy per array
+ * (UBLKCP, completion on a per-stage mbarrier); 0: by all lanes with 16-byte cp.async copies,
+ * three instructions per batch, in the same async-copy groups as the arrivals */
+#ifndef OWN_BULK
+#define OWN_BULK 1
+#endif
 
 /* Outbox: the particles that left their block in one push, one region per block and
  * destination code (geom.h), so that the receiving block finds its arrivals as
@@ -61,6 +67,7 @@ struct SpeciesDev {
 	int *count;              /* particles in the block's own segment */
 	Outbox ob[2];
 	int cap;                 /* slots per block segment */
+	unsigned astride;        /* doubles between the segment arrays x y ux uy uz id (one allocation) */
 	int ocs, occ;            /* slots per side / corner region */
 	int nob;                 /* blocks that own an outbox: the slab's, plus two ghost rows with several ranks */
 	unsigned roff[9];        /* first slot of the regions of code c */
@@ -167,6 +174,13 @@ __device__ __forceinline__ void
 cp_async8(void *dst, const void *src)
 {
 	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(smem_u32(dst)), "l"(src) : "memory");
+}
+
+/* 16-byte variant, L2 only (the segment batches are streamed once) */
+__device__ __forceinline__ void
+cp_async16(void *dst, const void *src)
+{
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_u32(dst)), "l"(src) : "memory");
 }
 
 __device__ __forceinline__ void
@@ -370,7 +384,7 @@ struct Arrivals {
 };
 
 __device__ __forceinline__ Arrivals
-find_arrivals(const Outbox &in, int sp_nob, const Geom &g, int nb, int b, int lane, int *scratch)
+find_arrivals(const int *__restrict__ in_count, int sp_nob, const Geom &g, int nb, int b, int lane, int *scratch)
 {
 	const int bx = b % g.nbx, by = b / g.nbx;
 	int src = 0, a_k = 0;
@@ -387,7 +401,7 @@ find_arrivals(const Outbox &in, int sp_nob, const Geom &g, int nb, int b, int la
 		else if(nby_ < 0) src = nb + nbx_;                 /* north ghost row */
 		else if(nby_ >= g.nby) src = nb + g.nbx + nbx_;    /* south ghost row */
 		else src = nby_ * g.nbx + nbx_;
-		a_k = in.count[(size_t) (8 - lane) * sp_nob + src];
+		a_k = in_count[(size_t) (8 - lane) * sp_nob + src];
 	}
 	int apre = a_k;
 	for(int o = 1; o < 16; o <<= 1)
@@ -404,14 +418,26 @@ find_arrivals(const Outbox &in, int sp_nob, const Geom &g, int nb, int b, int la
 	return A;
 }
 
+__device__ __forceinline__ Arrivals
+find_arrivals(const Outbox &in, int sp_nob, const Geom &g, int nb, int b, int lane, int *scratch)
+{
+	return find_arrivals(in.count, sp_nob, g, nb, b, lane, scratch);
+}
+
 /* Outbox slot of arrival f (0 <= f < A.total) */
 __device__ __forceinline__ unsigned
-arrival_slot(const Arrivals &A, const SpeciesDev &sp, int f)
+arrival_slot(const Arrivals &A, const unsigned *roff, const int *rcap, int f)
 {
 	int k = 0;
 #pragma unroll
 	for(int q = 1; q < 9; q++) if(f >= A.start[q]) k = q;
-	return region_slot(sp, 8 - k, A.src[k], f - A.start[k]);
+	return roff[8 - k] + (unsigned) A.src[k] * (unsigned) rcap[8 - k] + (unsigned) (f - A.start[k]);
+}
+
+__device__ __forceinline__ unsigned
+arrival_slot(const Arrivals &A, const SpeciesDev &sp, int f)
+{
+	return arrival_slot(A, sp.roff, sp.rcap, f);
 }
 
 /* Both components at once from the interleaved tile: the same products and sums, in the
@@ -518,7 +544,20 @@ k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 	const bool own_ = (bi) < nbo; \
 	double *st0_ = ring + ((bi) % PIPE_STAGES) * (NARR * 32); \
 	if(with_id) idmask |= 1u << ((bi) % PIPE_STAGES); else idmask &= ~(1u << ((bi) % PIPE_STAGES)); \
-	if(own_) { \
+	if(own_ && !OWN_BULK) { \
+		/* a whole batch of the segment is 256 contiguous, aligned bytes per array = 16 chunks of \
+		 * 16 B; chunk c (array c/16) is copied by lane c%32: x,y | ux,uy | uz,(id) | (E_x,E_y) */ \
+		const unsigned q_ = base + (bi) * 32 + (lane & 15) * 2; \
+		double *d_ = st0_ + lane * 2; \
+		const unsigned h_ = lane >> 4; \
+		cp_async16(d_, sp.x + (size_t) h_ * sp.astride + q_); \
+		if(MODE != 0) { \
+			cp_async16(d_ + 64, sp.x + (size_t) (2 + h_) * sp.astride + q_); \
+			if(h_ == 0 || (with_id)) cp_async16(d_ + 128, sp.x + (size_t) (4 + h_) * sp.astride + q_); \
+		} \
+		if(MODE == 1) cp_async16(d_ + 192, (h_ ? sp.pEy : sp.pEx) + q_); \
+		cp_async_commit(); \
+	} else if(own_) { \
 		/* a whole batch of the segment is 256 contiguous, aligned bytes per array: one TMA \
 		 * bulk copy each, issued by one lane, landing on the stage's mbarrier */ \
 		if(lane == 0) { \
@@ -597,11 +636,16 @@ k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 		/* batch bi has landed: segment batches on their stage barrier (its parity flips every
 		 * reuse), arrival batches when their own async-copy group is the oldest but
 		 * PIPE_STAGES-1 (every batch index >= nbo, real or not, commits exactly one group) */
-		if(own)
+		if(own && OWN_BULK)
 		{
 			if(mbar_wait(sbar + bi % PIPE_STAGES, (bi / PIPE_STAGES) & 1)) { atomicOr(errflag, ERRBIT_TMA); break; }
 		}
-		else cp_async_wait<PIPE_STAGES - 1>();
+		else
+		{
+			cp_async_wait<PIPE_STAGES - 1>();
+			/* a lane waits for its own copies only: the chunks of a segment batch were fetched by other lanes */
+			if(own) __syncwarp();
+		}
 
 		const double *st = ring + (bi % PIPE_STAGES) * (NARR * 32) + lane;
 		const bool have_id = (idmask >> (bi % PIPE_STAGES)) & 1;
@@ -977,22 +1021,44 @@ k_absorb(SpeciesDev sp, Geom g, int nb, int arr, int *__restrict__ errflag)
 }
 
 /* interpolate_p2f_rho, reference src/interpolate.c:282-346 / :161-276, accumulate-correct.
- * Each warp sums its block's particles (own segment, then the arrivals in outbox `arr`)
- * into private accumulators in shared memory: DEP_REP replicas (lane l uses replica
- * l % DEP_REP) of four arrays indexed by CELL, one per corner weight (w00, w01, w10, w11).
- * Two lanes can then only meet when they hold particles of the same cell in the same
- * replica; such lanes are ranked in lane order (match_any) and rank r adds in round r --
- * plain read-modify-write, race free, four independent updates per lane and round. Every
- * accumulator therefore has a fixed order of additions (batch, rank). The CTA finally
- * forms every node of its tile as the fixed-order sum of the (up to four) cells around it,
- * replicas in order, left block before right block, and stores: interior nodes to rho
- * (`=` for the first species, `+=` after), bottom row / right column / corner to the halo
- * arrays that k_stitch_* add in a fixed order. rho_reset (src/field.c:163-210) is implicit. */
+ * Each warp sums its block's particles -- species after species, own segment, then the
+ * arrivals pending in the outbox -- into private accumulators in shared memory: DEP_REP
+ * replicas (lane l uses replica l % DEP_REP) of four arrays indexed by CELL, one per corner
+ * weight (w00, w01, w10, w11). Two lanes can then only meet when they hold particles of the
+ * same cell in the same replica; such lanes are ranked in lane order (match_any) and rank r
+ * adds in round r -- plain read-modify-write, race free, four independent updates per lane
+ * and round. Every accumulator therefore has a fixed order of additions (species, batch,
+ * rank). The CTA finally forms every node of its tile as the fixed-order sum of the (up to
+ * four) cells around it, replicas in order, left block before right block, and stores:
+ * interior nodes to rho (`=` when FIRST, `+=` otherwise), bottom row / right column / corner
+ * to the halo arrays that k_stitch_* add in a fixed order. rho_reset (src/field.c:163-210)
+ * is implicit. One launch takes every species (DEP_FUSED), so that a block's accumulators
+ * are cleared, merged and stored once per step instead of once per species. */
 #define DEP_REP 2
+#define DEP_MAX_SPECIES 8
+#ifndef DEP_FUSED
+#define DEP_FUSED 1
+#endif
+
+/* What the deposit reads of one species */
+struct DepositSpecies {
+	const double *x, *y;     /* segments */
+	const int *count;
+	const double *ax, *ay;   /* the outbox that holds the pending arrivals */
+	const int *acount;
+	double vq;               /* -q / e0, reference src/interpolate.c:307 */
+	int cap, nob;
+	unsigned roff[9];
+	int rcap[9];
+};
+struct DepositSet {
+	DepositSpecies s[DEP_MAX_SPECIES];
+	int n;
+};
 
 template <bool FIRST>
 __global__ void __launch_bounds__(32 * MAX_WPC)
-k_deposit(SpeciesDev sp, Geom g, double vq, int nb, int arr,
+k_deposit(const __grid_constant__ DepositSet set, Geom g, int nb,
 		double *__restrict__ rho, double *__restrict__ hb, double *__restrict__ hr,
 		double *__restrict__ hc)
 {
@@ -1008,71 +1074,79 @@ k_deposit(SpeciesDev sp, Geom g, double vq, int nb, int arr,
 	const int bx = cx * g.WPC + warp;
 	const int b = by * g.nbx + bx;
 	double *t = acc + warp * wsz + (lane % DEP_REP) * 4 * NC;
-
-	__shared__ int scratch[MAX_WPC][18];
-	const Outbox &in = sp.ob[arr];
-	const Arrivals A = find_arrivals(in, sp.nob, g, nb, b, lane, scratch[warp]);
-	const int cnt = sp.count[b];
-	const int T = cnt + A.total;
-	const size_t base = (size_t) b * sp.cap;
 	const int cx0 = bx * g.BX, cy0 = by * g.BY;
 
-	double px = 0, py = 0;
-	if(lane < T)
-	{
-		if(lane < cnt) { px = sp.x[base + lane]; py = sp.y[base + lane]; }
-		else { const size_t so = arrival_slot(A, sp, lane - cnt); px = in.x[so]; py = in.y[so]; }
-	}
+	__shared__ int scratch[MAX_WPC][18];
 
 	for(int k = lane; k < wsz; k += 32) acc[warp * wsz + k] = 0.0;
 	__syncwarp();
 
-	for(int i0 = 0; i0 < T; i0 += 32)
+	for(int is = 0; is < set.n; is++)
 	{
-		const int i = i0 + lane;
-		const bool valid = i < T;
-		const double x = px, y = py;
-		if(i + 32 < T)
+		const DepositSpecies &sp = set.s[is];
+		const double *__restrict__ sx = sp.x, *__restrict__ sy = sp.y;
+		const double *__restrict__ ax = sp.ax, *__restrict__ ay = sp.ay;
+		const double vq = sp.vq;
+		__syncwarp();                /* the previous species' run table is no longer read */
+		const Arrivals A = find_arrivals(sp.acount, sp.nob, g, nb, b, lane, scratch[warp]);
+		const int cnt = sp.count[b];
+		const int T = cnt + A.total;
+		const size_t base = (size_t) b * sp.cap;
+
+		double px = 0, py = 0;
+		if(lane < T)
 		{
-			if(i + 32 < cnt) { px = sp.x[base + i + 32]; py = sp.y[base + i + 32]; }
-			else { const size_t so = arrival_slot(A, sp, i + 32 - cnt); px = in.x[so]; py = in.y[so]; }
+			if(lane < cnt) { px = sx[base + lane]; py = sy[base + lane]; }
+			else { const size_t so = arrival_slot(A, sp.roff, sp.rcap, lane - cnt); px = ax[so]; py = ay[so]; }
 		}
 
-		int key = -1 - lane;          /* unique key for idle lanes */
-		int cell = 0;
-		double a00 = 0, a01 = 0, a10 = 0, a11 = 0;
-		if(valid)
+		for(int i0 = 0; i0 < T; i0 += 32)
 		{
-			int i0x, i0y;
-			double w00, w01, w10, w11;
-			cic_weights(g, x, y, i0x, i0y, w00, w01, w10, w11);
-			a00 = MUL(w00, vq); a01 = MUL(w01, vq); a10 = MUL(w10, vq); a11 = MUL(w11, vq);
-			cell = ((i0y - cy0) << g.lBX) + (i0x - cx0);
-			key = cell * DEP_REP + lane % DEP_REP;
-		}
-		const unsigned peers = __match_any_sync(FULL, key);
-		const int rank = __popc(peers & lt);
-		const int rounds = __reduce_max_sync(FULL, valid ? rank + 1 : 0);
-		for(int r = 0; r < rounds; r++)
-		{
-			if(valid && rank == r)
+			const int i = i0 + lane;
+			const bool valid = i < T;
+			const double x = px, y = py;
+			if(i + 32 < T)
 			{
-#if DEP_RECORDS
-				double2 *rec = (double2 *) (t + 4 * cell);       /* {w00, w01}, {w10, w11} sums of the cell */
-				double2 v0 = rec[0], v1 = rec[1];
-				v0.x = ADD(v0.x, a00); v0.y = ADD(v0.y, a01);
-				v1.x = ADD(v1.x, a10); v1.y = ADD(v1.y, a11);
-				rec[0] = v0;
-				rec[1] = v1;
-#else
-				const double v0 = t[cell], v1 = t[NC + cell], v2 = t[2 * NC + cell], v3 = t[3 * NC + cell];
-				t[cell] = ADD(v0, a00);
-				t[NC + cell] = ADD(v1, a01);
-				t[2 * NC + cell] = ADD(v2, a10);
-				t[3 * NC + cell] = ADD(v3, a11);
-#endif
+				if(i + 32 < cnt) { px = sx[base + i + 32]; py = sy[base + i + 32]; }
+				else { const size_t so = arrival_slot(A, sp.roff, sp.rcap, i + 32 - cnt); px = ax[so]; py = ay[so]; }
 			}
-			__syncwarp();
+
+			int key = -1 - lane;          /* unique key for idle lanes */
+			int cell = 0;
+			double a00 = 0, a01 = 0, a10 = 0, a11 = 0;
+			if(valid)
+			{
+				int i0x, i0y;
+				double w00, w01, w10, w11;
+				cic_weights(g, x, y, i0x, i0y, w00, w01, w10, w11);
+				a00 = MUL(w00, vq); a01 = MUL(w01, vq); a10 = MUL(w10, vq); a11 = MUL(w11, vq);
+				cell = ((i0y - cy0) << g.lBX) + (i0x - cx0);
+				key = cell * DEP_REP + lane % DEP_REP;
+			}
+			const unsigned peers = __match_any_sync(FULL, key);
+			const int rank = __popc(peers & lt);
+			const int rounds = __reduce_max_sync(FULL, valid ? rank + 1 : 0);
+			for(int r = 0; r < rounds; r++)
+			{
+				if(valid && rank == r)
+				{
+#if DEP_RECORDS
+					double2 *rec = (double2 *) (t + 4 * cell);       /* {w00, w01}, {w10, w11} sums of the cell */
+					double2 v0 = rec[0], v1 = rec[1];
+					v0.x = ADD(v0.x, a00); v0.y = ADD(v0.y, a01);
+					v1.x = ADD(v1.x, a10); v1.y = ADD(v1.y, a11);
+					rec[0] = v0;
+					rec[1] = v1;
+#else
+					const double v0 = t[cell], v1 = t[NC + cell], v2 = t[2 * NC + cell], v3 = t[3 * NC + cell];
+					t[cell] = ADD(v0, a00);
+					t[NC + cell] = ADD(v1, a01);
+					t[2 * NC + cell] = ADD(v2, a10);
+					t[3 * NC + cell] = ADD(v3, a11);
+#endif
+				}
+				__syncwarp();
+			}
 		}
 	}
 

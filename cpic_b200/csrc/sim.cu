@@ -1,7 +1,9 @@
 /* cpic_b200: simulation context, stage orchestration and the C ABI (include/cpic_b200.h).
  *
  * Stage order and semantics follow the reference's sim_step (src/sim.c:481-581); every
- * entry point names the reference function it replaces. Device work goes to one stream.
+ * entry point names the reference function it replaces. Device work goes to one stream;
+ * the pushes of the odd species run on a second one so that the last, partly filled wave
+ * of one species' CTAs overlaps the first wave of the next.
  */
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -68,6 +70,9 @@ struct cpic_b200_sim {
 	long long iter;
 	double umax[3];
 	cudaStream_t stream;
+	cudaStream_t stream2;    /* pushes of the odd species (forked from / joined into `stream`) */
+	cudaEvent_t ev_fork, ev_join;
+	bool overlap_species;
 	int device;
 
 	double *rho, *phi, *phi_raw, *Ex, *Ey, *G;
@@ -233,6 +238,13 @@ cpic_b200_create(const cpic_b200_params_t *pp, cpic_b200_sim_t **out)
 	cpic_b200_destroy(s); return rc_; } } while(0)
 
 	CKD(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+	CKD(cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking));
+	CKD(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
+	CKD(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
+	{
+		const char *e = getenv("CPIC_B200_OVERLAP_SPECIES");
+		s->overlap_species = !(e && atoi(e) == 0);
+	}
 	CKD(cudaEventCreate(&s->ev[0]));
 	CKD(cudaEventCreate(&s->ev[1]));
 
@@ -337,6 +349,9 @@ cpic_b200_destroy(cpic_b200_sim_t *s)
 	if(s->ev[0]) cudaEventDestroy(s->ev[0]);
 	if(s->ev[1]) cudaEventDestroy(s->ev[1]);
 	if(s->stream) cudaStreamDestroy(s->stream);
+	if(s->stream2) cudaStreamDestroy(s->stream2);
+	if(s->ev_fork) cudaEventDestroy(s->ev_fork);
+	if(s->ev_join) cudaEventDestroy(s->ev_join);
 	delete s;
 }
 
@@ -368,6 +383,7 @@ alloc_species(sim_t_ *s, int is, int cap)
 	h.d.id = (long long *) (b + 5 * arr);
 	h.d.count = (int *) (b + 6 * arr);
 	h.d.cap = cap;
+	h.d.astride = (unsigned) (arr / sizeof(double));
 
 	/* outbox regions: four sides of ocs slots, four corners of occ, stored code-major */
 	double frac = s->p.outbox_fraction > 0 ? s->p.outbox_fraction : 0.3;
@@ -862,7 +878,7 @@ push_params(const sim_t_ *s, int is)
 
 template <int MODE>
 static int
-launch_gather_push(sim_t_ *s, int is)
+launch_gather_push(sim_t_ *s, int is, cudaStream_t stream)
 {
 	SpeciesHost &h = s->sp[is];
 	if(!h.block) return 0;
@@ -878,7 +894,7 @@ launch_gather_push(sim_t_ *s, int is)
 	const int ctas = s->nb / g.WPC;
 	/* a push reads the pending arrivals and fills the other outbox */
 	const int cur = MODE == 0 ? h.arr : h.arr ^ 1;
-	k_gather_push<MODE><<<ctas, 32 * g.WPC, smem, s->stream>>>(h.d, g, push_params(s, is),
+	k_gather_push<MODE><<<ctas, 32 * g.WPC, smem, stream>>>(h.d, g, push_params(s, is),
 			s->mapEx, s->mapEy, s->nb, cur, s->errflag);
 	if(MODE != 0) h.arr = cur;
 	return check_launch(s);
@@ -894,7 +910,7 @@ cpic_b200_stage_plasma_E(cpic_b200_sim_t *s)
 	for(int is = 0; is < s->p.nspecies; is++)
 	{
 		int rc = ensure_particle_E(s, is);
-		if(!rc) rc = launch_gather_push<0>(s, is);
+		if(!rc) rc = launch_gather_push<0>(s, is, s->stream);
 		if(rc) return rc;
 	}
 	return 0;
@@ -943,12 +959,26 @@ stage_plasma_r(sim_t_ *s)
 {
 	{
 		StageTimer t(s, T_PUSH);
+		/* species are independent until the exchange: odd ones go to the second stream */
+		const bool fork = s->overlap_species && s->p.nspecies > 1;
+		if(fork)
+		{
+			for(int is = 0; is < s->p.nspecies; is++)
+				if(MODE == 1) { int rc = ensure_particle_E(s, is); if(rc) return rc; }
+			CK(cudaEventRecord(s->ev_fork, s->stream));
+			CK(cudaStreamWaitEvent(s->stream2, s->ev_fork, 0));
+		}
 		for(int is = 0; is < s->p.nspecies; is++)
 		{
 			int rc = 0;
-			if(MODE == 1) rc = ensure_particle_E(s, is);
-			if(!rc) rc = launch_gather_push<MODE>(s, is);
+			if(MODE == 1 && !fork) rc = ensure_particle_E(s, is);
+			if(!rc) rc = launch_gather_push<MODE>(s, is, (fork && (is & 1)) ? s->stream2 : s->stream);
 			if(rc) return rc;
+		}
+		if(fork)
+		{
+			CK(cudaEventRecord(s->ev_join, s->stream2));
+			CK(cudaStreamWaitEvent(s->stream, s->ev_join, 0));
 		}
 	}
 	return exchange(s);
@@ -980,17 +1010,41 @@ cpic_b200_stage_field_rho(cpic_b200_sim_t *s)
 		CK(cudaFuncSetAttribute(k_deposit<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) s->smem_dep));
 		dep_attr = s->smem_dep;
 	}
+	static_assert(DEP_MAX_SPECIES >= CPIC_B200_MAX_SPECIES, "deposit set too small");
+	DepositSet set;
+	set.n = 0;
 	for(int is = 0; is < s->p.nspecies; is++)
 	{
 		SpeciesHost &h = s->sp[is];
 		if(!h.block) continue;
-		const double vq = -h.q / s->p.e0;       /* reference src/interpolate.c:307 */
-		if(first) k_deposit<true><<<ctas, 32 * g.WPC, s->smem_dep, s->stream>>>(h.d, g, vq, s->nb, h.arr, s->rho, s->hb, s->hr, s->hc);
-		else k_deposit<false><<<ctas, 32 * g.WPC, s->smem_dep, s->stream>>>(h.d, g, vq, s->nb, h.arr, s->rho, s->hb, s->hr, s->hc);
+		DepositSpecies &d = set.s[set.n++];
+		const Outbox &in = h.d.ob[h.arr];
+		d.x = h.d.x; d.y = h.d.y; d.count = h.d.count;
+		d.ax = in.x; d.ay = in.y; d.acount = in.count;
+		d.vq = -h.q / s->p.e0;       /* reference src/interpolate.c:307 */
+		d.cap = h.d.cap; d.nob = h.d.nob;
+		memcpy(d.roff, h.d.roff, sizeof(d.roff));
+		memcpy(d.rcap, h.d.rcap, sizeof(d.rcap));
 		first = false;
+	}
+	if(set.n && DEP_FUSED)
+	{
+		/* every species in one pass over the blocks */
+		k_deposit<true><<<ctas, 32 * g.WPC, s->smem_dep, s->stream>>>(set, g, s->nb, s->rho, s->hb, s->hr, s->hc);
 		int rc = check_launch(s);
 		if(rc) return rc;
 	}
+	else
+		for(int k = 0; k < set.n; k++)
+		{
+			DepositSet one;
+			one.s[0] = set.s[k];
+			one.n = 1;
+			if(k == 0) k_deposit<true><<<ctas, 32 * g.WPC, s->smem_dep, s->stream>>>(one, g, s->nb, s->rho, s->hb, s->hr, s->hc);
+			else k_deposit<false><<<ctas, 32 * g.WPC, s->smem_dep, s->stream>>>(one, g, s->nb, s->rho, s->hb, s->hr, s->hc);
+			int rc = check_launch(s);
+			if(rc) return rc;
+		}
 	if(first)
 	{
 		/* no particles at all: rho_reset only */

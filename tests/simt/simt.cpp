@@ -250,6 +250,12 @@ async_copy8(void *dst, const void *src)
 }
 
 void
+misuse(const char *what)
+{
+	fatal("%s", what);
+}
+
+void
 async_commit()
 {
 	cur->groups.emplace_back();
@@ -570,6 +576,8 @@ cudaError_t cudaStreamDestroy(cudaStream_t s) { delete s; return cudaSuccess; }
 cudaError_t cudaStreamSynchronize(cudaStream_t) { return simt::aborting ? 700 : cudaSuccess; }
 cudaError_t cudaDeviceSynchronize(void) { return simt::aborting ? 700 : cudaSuccess; }
 cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = new simt_event_(); return cudaSuccess; }
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { *e = new simt_event_(); return cudaSuccess; }
+cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
 cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
 
 cudaError_t

@@ -66,6 +66,7 @@ void yield();
 /* asynchronous copies, completed at the wait */
 void async_copy8(void *dst, const void *src);
 void async_commit();
+void misuse(const char *what);
 void async_wait(int keep_newest);
 void bar_init(uint64_t *bar, int count);
 void bar_expect_tx(uint64_t *bar, uint32_t bytes);
@@ -137,7 +138,10 @@ cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned flags);
 cudaError_t cudaStreamDestroy(cudaStream_t s);
 cudaError_t cudaStreamSynchronize(cudaStream_t s);
 cudaError_t cudaDeviceSynchronize(void);
+enum { cudaEventDefault = 0, cudaEventDisableTiming = 2 };
 cudaError_t cudaEventCreate(cudaEvent_t *e);
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned flags);
+cudaError_t cudaStreamWaitEvent(cudaStream_t s, cudaEvent_t e, unsigned flags = 0);
 cudaError_t cudaEventDestroy(cudaEvent_t e);
 cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s = 0);
 cudaError_t cudaEventSynchronize(cudaEvent_t e);

@@ -22,6 +22,12 @@ mbar_wait(uint64_t *bar, uint32_t parity)
 static inline void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) { simt::bar_tensor_load_2d(dst, map, c0, c1, bar); }
 static inline void tma_bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) { simt::bar_bulk_load(dst, src, bytes, bar); }
 static inline void cp_async8(void *dst, const void *src) { simt::async_copy8(dst, src); }
+static inline void cp_async16(void *dst, const void *src)
+{
+	if((uintptr_t) dst % 16 || (uintptr_t) src % 16) simt::misuse("cp.async 16 needs 16-byte aligned addresses");
+	simt::async_copy8(dst, src);
+	simt::async_copy8((char *) dst + 8, (const char *) src + 8);
+}
 static inline void cp_async_commit() { simt::async_commit(); }
 template <int N> static inline void cp_async_wait() { simt::async_wait(N); }
 
