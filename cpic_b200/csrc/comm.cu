@@ -247,29 +247,14 @@ comm_phi_halo(Comm *c, double *phi, cudaStream_t stream)
 #define FAR_SECTION (1 + 8 * FAR_FACE)      /* doubles: count, then eight arrays */
 
 /* Pack / unpack of the regions that cross a slab face. A face buffer holds, for the three
- * codes k of that direction and the NA arrays (x y ux uy uz id [Ex Ey]), the regions of
- * the nbx edge blocks (nbx * rcap[code] values each), followed by the 3 * nbx counts. */
+ * codes k of that direction, the records of the nbx edge blocks' regions (nbx * rcap[code]
+ * records of OREC doubles, one contiguous chunk of the outbox), then their (E_x, E_y) pairs
+ * when the per-particle field is kept, followed by the 3 * nbx counts. */
 struct FaceLayout {
-	unsigned off[3];         /* first value of code k's chunk (per array: nbx * rcap values) */
+	unsigned off[3];         /* first value of code k's chunk */
 	unsigned total;          /* doubles before the counts */
-	int na;
+	int na;                  /* doubles per slot: OREC, + 2 with the field */
 };
-
-static __device__ __forceinline__ double *
-outbox_array(const Outbox &ob, int a)
-{
-	switch(a)
-	{
-		case 0: return ob.x;
-		case 1: return ob.y;
-		case 2: return ob.ux;
-		case 3: return ob.uy;
-		case 4: return ob.uz;
-		case 5: return (double *) ob.id;
-		case 6: return ob.Ex;
-		default: return ob.Ey;
-	}
-}
 
 /* dir 0: row 0, codes 0,1,2 (to the north rank); dir 1: last row, codes 6,7,8 (south).
  * pack != 0: regions -> buffer; else buffer -> ghost rows (north buffer received from the
@@ -284,11 +269,10 @@ k_face_copy(SpeciesDev sp, int arr, int nbx, int first_block, int code0, FaceLay
 	{
 		int k = i >= L.off[2] ? 2 : i >= L.off[1] ? 1 : 0;
 		const int c = code0 + k;
-		const unsigned per = (unsigned) nbx * (unsigned) sp.rcap[c];      /* values per array */
-		const unsigned r = i - L.off[k];
-		const int a = r / per;
-		const unsigned j = r % per;                                       /* block-major inside the row */
-		double *p = outbox_array(ob, a) + sp.roff[c] + (unsigned) first_block * (unsigned) sp.rcap[c] + j;
+		const size_t slots = (size_t) nbx * (size_t) sp.rcap[c];          /* block-major inside the row */
+		const size_t slot0 = (size_t) sp.roff[c] + (size_t) first_block * (size_t) sp.rcap[c];
+		const size_t r = i - L.off[k];
+		double *p = r < slots * OREC ? ob.rec + slot0 * OREC + r : ob.recE + slot0 * 2 + (r - slots * OREC);
 		if(pack) buf[i] = *p;
 		else *p = buf[i];
 	}
@@ -307,7 +291,7 @@ static FaceLayout
 face_layout(const SpeciesDev *sp, int nbx, int code0)
 {
 	FaceLayout L;
-	L.na = sp->ob[0].Ex ? 8 : 6;
+	L.na = sp->ob[0].recE ? OREC + 2 : OREC;
 	unsigned off = 0;
 	for(int k = 0; k < 3; k++)
 	{

@@ -46,16 +46,19 @@
 
 /* Outbox: the particles that left their block in one push, one region per block and
  * destination code (geom.h), so that the receiving block finds its arrivals as
- * contiguous runs. Regions are stored code-major -- all blocks' code-0 regions, then all
- * code-1 regions ... -- so that what one block row sends across a slab face (codes 0,1,2
- * of row 0, codes 6,7,8 of the last row) is three contiguous chunks per array and can be
- * handed to NCCL without packing. Side regions (codes 1,3,5,7) hold `ocs` slots, corner
+ * contiguous runs. A slot is one 48-byte record (x y ux uy uz id): a leaver is written
+ * with three 16-byte stores and the leavers of a block for one destination fill
+ * consecutive records, so the few dozen particles a region receives per step are one
+ * contiguous run in memory instead of one short run in each of six arrays. Regions are
+ * stored code-major -- all blocks' code-0 regions, then all code-1 regions ... -- so that
+ * what one block row sends across a slab face (codes 0,1,2 of row 0, codes 6,7,8 of the last
+ * row) is three contiguous chunks. Side regions (codes 1,3,5,7) hold `ocs` slots, corner
  * regions (0,2,6,8) `occ`. Two outboxes alternate: a push reads the arrivals of the
  * previous push from one and fills the other. */
+#define OREC 6                   /* doubles per outbox record */
 struct Outbox {
-	double *x, *y, *ux, *uy, *uz;
-	double *Ex, *Ey;         /* travel with the particle when the per-particle E is kept */
-	long long *id;
+	double *rec;             /* [slot][x y ux uy uz id] */
+	double *recE;            /* [slot][Ex Ey]: travels with the particle when the per-particle E is kept */
 	int *count;              /* [code][block]: leavers of that block with that destination */
 };
 
@@ -571,15 +574,16 @@ k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 			if(MODE == 1) { tma_bulk_load(st0_ + 6 * 32, sp.pEx + q_, 256, mb_); tma_bulk_load(st0_ + 7 * 32, sp.pEy + q_, 256, mb_); } \
 		} \
 	} else { \
-		/* arrivals are scattered over up to eight runs: per-lane 8-byte async copies */ \
+		/* arrivals are scattered over up to eight runs of records: per lane three 16-byte async \
+		 * copies, landing as (x,y) (ux,uy) (uz,id) pairs, lane l at doubles 2l, 2l+1 of each array pair */ \
 		const int t_ = ((bi) - nbo) * 32 + lane; \
-		double *st_ = st0_ + lane; \
+		double *st_ = st0_ + 2 * lane; \
 		if(t_ < A.total) { \
-			const unsigned q_ = (unsigned) arrival_slot(A, sp, t_); \
-			cp_async8(st_ + 0 * 32, in.x + q_); cp_async8(st_ + 1 * 32, in.y + q_); \
-			if(MODE != 0) { cp_async8(st_ + 2 * 32, in.ux + q_); cp_async8(st_ + 3 * 32, in.uy + q_); \
-				cp_async8(st_ + 4 * 32, in.uz + q_); if(with_id) cp_async8(st_ + 5 * 32, in.id + q_); } \
-			if(MODE == 1) { cp_async8(st_ + 6 * 32, in.Ex + q_); cp_async8(st_ + 7 * 32, in.Ey + q_); } \
+			const size_t q_ = arrival_slot(A, sp, t_); \
+			const double *r_ = in.rec + q_ * OREC; \
+			cp_async16(st_, r_); \
+			if(MODE != 0) { cp_async16(st_ + 64, r_ + 2); cp_async16(st_ + 128, r_ + 4); } \
+			if(MODE == 1) cp_async16(st_ + 192, in.recE + q_ * 2); \
 		} \
 		cp_async_commit(); \
 	} } while(0)
@@ -647,7 +651,10 @@ k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 			if(own) __syncwarp();
 		}
 
-		const double *st = ring + (bi % PIPE_STAGES) * (NARR * 32) + lane;
+		/* a segment batch is staged array by array (lane l at l of each), an arrival batch
+		 * record by record (lane l at 2l, 2l+1 of each array pair) */
+		const double *st = ring + (bi % PIPE_STAGES) * (NARR * 32);
+		const int e0 = own ? lane : 2 * lane, e1 = own ? 32 + lane : 2 * lane + 1;
 		const bool have_id = (idmask >> (bi % PIPE_STAGES)) & 1;
 		/* source slot: needed for the E store of MODE 0 and the late id fetch (segment only) */
 		const unsigned s = own ? base + t : ((MODE == 0 && valid) ? (unsigned) arrival_slot(A, sp, t) : 0u);
@@ -655,9 +662,9 @@ k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 		long long pid = 0;
 		if(valid)
 		{
-			x = st[0 * 32]; y = st[1 * 32];
-			if(MODE != 0) { ux = st[2 * 32]; uy = st[3 * 32]; uz = st[4 * 32]; if(have_id) pid = __double_as_longlong(st[5 * 32]); }
-			if(MODE == 1) { Ex = st[6 * 32]; Ey = st[7 * 32]; }
+			x = st[e0]; y = st[e1];
+			if(MODE != 0) { ux = st[64 + e0]; uy = st[64 + e1]; uz = st[128 + e0]; if(have_id) pid = __double_as_longlong(st[128 + e1]); }
+			if(MODE == 1) { Ex = st[192 + e0]; Ey = st[192 + e1]; }
 		}
 
 		if(MODE != 1 && valid)
@@ -674,7 +681,7 @@ k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 			if(MODE == 0)
 			{
 				if(own) { sp.pEx[s] = Ex; sp.pEy[s] = Ey; }
-				else { in.Ex[s] = Ex; in.Ey[s] = Ey; }
+				else *(double2 *) (in.recE + (size_t) s * 2) = make_double2(Ex, Ey);
 			}
 		}
 
@@ -755,11 +762,12 @@ k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 				}
 				else if(pos < sp.rcap[dest])
 				{
-					const unsigned o = region_slot(sp, dest, b, pos);
-					out.x[o] = x; out.y[o] = y;
-					out.ux[o] = ux; out.uy[o] = uy; out.uz[o] = uz;
-					out.id[o] = pid;
-					if(out.Ex) { out.Ex[o] = Ex; out.Ey[o] = Ey; }
+					const size_t o = region_slot(sp, dest, b, pos);
+					double2 *r = (double2 *) (out.rec + o * OREC);
+					r[0] = make_double2(x, y);
+					r[1] = make_double2(ux, uy);
+					r[2] = make_double2(uz, __longlong_as_double(pid));
+					if(out.recE) *(double2 *) (out.recE + o * 2) = make_double2(Ex, Ey);
 				}
 				else bad |= 8;
 			}
@@ -974,10 +982,11 @@ k_regrow(SpeciesDev sp, SpeciesDev dst, Geom g, int nb, int arr)
 		else
 		{
 			const size_t s = arrival_slot(A, sp, i - cnt);
-			dst.x[d] = in.x[s]; dst.y[d] = in.y[s];
-			dst.ux[d] = in.ux[s]; dst.uy[d] = in.uy[s]; dst.uz[d] = in.uz[s];
-			dst.id[d] = in.id[s];
-			if(dst.pEx && in.Ex) { dst.pEx[d] = in.Ex[s]; dst.pEy[d] = in.Ey[s]; }
+			const double *r = in.rec + s * OREC;
+			dst.x[d] = r[0]; dst.y[d] = r[1];
+			dst.ux[d] = r[2]; dst.uy[d] = r[3]; dst.uz[d] = r[4];
+			dst.id[d] = __double_as_longlong(r[5]);
+			if(dst.pEx && in.recE) { dst.pEx[d] = in.recE[s * 2]; dst.pEy[d] = in.recE[s * 2 + 1]; }
 		}
 	}
 	if(lane == 0) dst.count[b] = min(cnt + A.total, dst.cap);
@@ -1006,10 +1015,11 @@ k_absorb(SpeciesDev sp, Geom g, int nb, int arr, int *__restrict__ errflag)
 	for(int f = lane; f < A.total; f += 32)
 	{
 		const size_t so = arrival_slot(A, sp, f), d = base + cnt + f;
-		sp.x[d] = in.x[so]; sp.y[d] = in.y[so];
-		sp.ux[d] = in.ux[so]; sp.uy[d] = in.uy[so]; sp.uz[d] = in.uz[so];
-		sp.id[d] = in.id[so];
-		if(sp.pEx) { sp.pEx[d] = in.Ex[so]; sp.pEy[d] = in.Ey[so]; }
+		const double *r = in.rec + so * OREC;
+		sp.x[d] = r[0]; sp.y[d] = r[1];
+		sp.ux[d] = r[2]; sp.uy[d] = r[3]; sp.uz[d] = r[4];
+		sp.id[d] = __double_as_longlong(r[5]);
+		if(sp.pEx) { sp.pEx[d] = in.recE[so * 2]; sp.pEy[d] = in.recE[so * 2 + 1]; }
 	}
 	__syncwarp();                /* every lane has read the old count */
 	if(lane == 0) sp.count[b] = cnt + A.total;
@@ -1044,7 +1054,7 @@ k_absorb(SpeciesDev sp, Geom g, int nb, int arr, int *__restrict__ errflag)
 struct DepositSpecies {
 	const double *x, *y;     /* segments */
 	const int *count;
-	const double *ax, *ay;   /* the outbox that holds the pending arrivals */
+	const double *arec;      /* the outbox that holds the pending arrivals (records, x y first) */
 	const int *acount;
 	double vq;               /* -q / e0, reference src/interpolate.c:307 */
 	int cap, nob;
@@ -1085,7 +1095,7 @@ k_deposit(const __grid_constant__ DepositSet set, Geom g, int nb,
 	{
 		const DepositSpecies &sp = set.s[is];
 		const double *__restrict__ sx = sp.x, *__restrict__ sy = sp.y;
-		const double *__restrict__ ax = sp.ax, *__restrict__ ay = sp.ay;
+		const double *__restrict__ arec = sp.arec;
 		const double vq = sp.vq;
 		__syncwarp();                /* the previous species' run table is no longer read */
 		const Arrivals A = find_arrivals(sp.acount, sp.nob, g, nb, b, lane, scratch[warp]);
@@ -1097,7 +1107,11 @@ k_deposit(const __grid_constant__ DepositSet set, Geom g, int nb,
 		if(lane < T)
 		{
 			if(lane < cnt) { px = sx[base + lane]; py = sy[base + lane]; }
-			else { const size_t so = arrival_slot(A, sp.roff, sp.rcap, lane - cnt); px = ax[so]; py = ay[so]; }
+			else
+			{
+				const double2 v = *(const double2 *) (arec + (size_t) arrival_slot(A, sp.roff, sp.rcap, lane - cnt) * OREC);
+				px = v.x; py = v.y;
+			}
 		}
 
 		for(int i0 = 0; i0 < T; i0 += 32)
@@ -1108,7 +1122,11 @@ k_deposit(const __grid_constant__ DepositSet set, Geom g, int nb,
 			if(i + 32 < T)
 			{
 				if(i + 32 < cnt) { px = sx[base + i + 32]; py = sy[base + i + 32]; }
-				else { const size_t so = arrival_slot(A, sp.roff, sp.rcap, i + 32 - cnt); px = ax[so]; py = ay[so]; }
+				else
+				{
+					const double2 v = *(const double2 *) (arec + (size_t) arrival_slot(A, sp.roff, sp.rcap, i + 32 - cnt) * OREC);
+					px = v.x; py = v.y;
+				}
 			}
 
 			int key = -1 - lane;          /* unique key for idle lanes */

@@ -404,23 +404,18 @@ alloc_species(sim_t_ *s, int is, int cap)
 		off += (unsigned) s->nob * (unsigned) h.d.rcap[c];
 	}
 	const size_t oslot = off;
-	const size_t oarr = align256(oslot * sizeof(double));
+	const size_t orec = align256(oslot * OREC * sizeof(double));
 	const size_t ocnt = align256((size_t) s->nob * 9 * sizeof(int));
-	const size_t one = 6 * oarr + ocnt;
+	const size_t one = orec + ocnt;
 	CK(cudaMalloc(&h.oblock, 2 * one));
 	CK(cudaMemsetAsync(h.oblock, 0, 2 * one, s->stream));
 	for(int k = 0; k < 2; k++)
 	{
 		char *o = (char *) h.oblock + k * one;
 		Outbox &ob = h.d.ob[k];
-		ob.x = (double *) (o + 0 * oarr);
-		ob.y = (double *) (o + 1 * oarr);
-		ob.ux = (double *) (o + 2 * oarr);
-		ob.uy = (double *) (o + 3 * oarr);
-		ob.uz = (double *) (o + 4 * oarr);
-		ob.id = (long long *) (o + 5 * oarr);
-		ob.count = (int *) (o + 6 * oarr);
-		ob.Ex = ob.Ey = NULL;
+		ob.rec = (double *) o;
+		ob.count = (int *) (o + orec);
+		ob.recE = NULL;
 	}
 	h.arr = 0;
 
@@ -450,16 +445,14 @@ ensure_particle_E(sim_t_ *s, int is)
 	SpeciesHost &h = s->sp[is];
 	if(h.d.pEx || !h.block) return 0;
 	const size_t arr = align256((size_t) s->nb * h.d.cap * sizeof(double));
-	const size_t oarr = align256(((size_t) h.d.roff[8] + (size_t) s->nob * h.d.rcap[8]) * sizeof(double));
-	CK(cudaMalloc(&h.pE, 2 * arr + 4 * oarr));
-	CK(cudaMemsetAsync(h.pE, 0, 2 * arr + 4 * oarr, s->stream));
+	/* (E_x, E_y) per outbox slot, next to the records */
+	const size_t oarr = align256(((size_t) h.d.roff[8] + (size_t) s->nob * h.d.rcap[8]) * 2 * sizeof(double));
+	CK(cudaMalloc(&h.pE, 2 * arr + 2 * oarr));
+	CK(cudaMemsetAsync(h.pE, 0, 2 * arr + 2 * oarr, s->stream));
 	h.d.pEx = h.pE;
 	h.d.pEy = (double *) ((char *) h.pE + arr);
 	for(int k = 0; k < 2; k++)
-	{
-		h.d.ob[k].Ex = (double *) ((char *) h.pE + 2 * arr + (2 * k) * oarr);
-		h.d.ob[k].Ey = (double *) ((char *) h.pE + 2 * arr + (2 * k + 1) * oarr);
-	}
+		h.d.ob[k].recE = (double *) ((char *) h.pE + 2 * arr + k * oarr);
 	return 0;
 }
 
@@ -1020,7 +1013,7 @@ cpic_b200_stage_field_rho(cpic_b200_sim_t *s)
 		DepositSpecies &d = set.s[set.n++];
 		const Outbox &in = h.d.ob[h.arr];
 		d.x = h.d.x; d.y = h.d.y; d.count = h.d.count;
-		d.ax = in.x; d.ay = in.y; d.acount = in.count;
+		d.arec = in.rec; d.acount = in.count;
 		d.vq = -h.q / s->p.e0;       /* reference src/interpolate.c:307 */
 		d.cap = h.d.cap; d.nob = h.d.nob;
 		memcpy(d.roff, h.d.roff, sizeof(d.roff));
