@@ -262,8 +262,10 @@ k_field_E(const double *__restrict__ phi, double *__restrict__ Ex, double *__res
 	const double ex = (p[x0] - p[x1]) / dx2;
 	Ey[(size_t) iy * g.SE + ix] = ey;
 	Ex[(size_t) iy * g.SE + ix] = ex;
+#if E_INTERLEAVED
 	/* the copy the particle kernels fetch their tiles from: (E_x, E_y) side by side */
 	Exy[(size_t) iy * g.SE + ix] = make_double2(ex, ey);
+#endif
 }
 
 /* (E_x, E_y) pairs from the two separate arrays (after cpic_b200_set_field) */
