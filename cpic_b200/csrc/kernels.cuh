@@ -743,12 +743,19 @@ k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 		const unsigned ml = __ballot_sync(FULL, leave);
 		if(ml)
 		{
+			/* the leavers that share my destination: one ballot per bit of the code (0..9) */
+			unsigned peers = ml;
+#pragma unroll
+			for(int k = 0; k < 4; k++)
+			{
+				const unsigned bk = __ballot_sync(FULL, leave && ((dest >> k) & 1));
+				peers &= ((dest >> k) & 1) ? bk : ~bk;
+			}
+			/* rank inside the destination region: batches in order, lanes in order */
+			const int pos = leave ? ocnt[dest] + __popc(peers & lt) : 0;
+			__syncwarp();
 			if(leave)
 			{
-				/* rank inside the destination region: batches in order, lanes in order */
-				const unsigned peers = __match_any_sync(ml, dest);
-				const int pos = ocnt[dest] + __popc(peers & lt);
-				__syncwarp(ml);
 				if((peers & lt) == 0) ocnt[dest] = pos + __popc(peers);
 				if(dest == DEST_FAR)
 				{
@@ -1037,10 +1044,10 @@ k_absorb(SpeciesDev sp, Geom g, int nb, int arr, int *__restrict__ errflag)
  * arrivals pending in the outbox -- into private accumulators in shared memory: DEP_REP
  * replicas (lane l uses replica l % DEP_REP) of four arrays indexed by CELL, one per corner
  * weight (w00, w01, w10, w11). Two lanes can then only meet when they hold particles of the
- * same cell in the same replica; such lanes are ranked in lane order (match_any) and rank r
- * adds in round r -- plain read-modify-write, race free, four independent updates per lane
- * and round. Every accumulator therefore has a fixed order of additions (species, batch,
- * rank). The CTA finally forms every node of its tile as the fixed-order sum of the (up to
+ * same cell in the same replica; such lanes are found with ballots, the first of them adds up
+ * the group's contributions in lane order (shuffles) and alone updates the accumulators --
+ * plain read-modify-write, race free, four independent updates per lane. Every accumulator
+ * therefore has a fixed order of additions (species, batch, lane). The CTA finally forms every node of its tile as the fixed-order sum of the (up to
  * four) cells around it, replicas in order, left block before right block, and stores:
  * interior nodes to rho (`=` when FIRST, `+=` otherwise), bottom row / right column / corner
  * to the halo arrays that k_stitch_* add in a fixed order. rho_reset (src/field.c:163-210)
@@ -1087,6 +1094,9 @@ k_deposit(const __grid_constant__ DepositSet set, Geom g, int nb,
 	const int b = by * g.nbx + bx;
 	double *t = acc + warp * wsz + (lane % DEP_REP) * 4 * NC;
 	const int cx0 = bx * g.BX, cy0 = by * g.BY;
+	const int cbits = g.lBX + g.lBY;             /* bits of a cell index */
+	static_assert(DEP_REP == 1 || DEP_REP == 2, "replica masks are written for one or two replicas");
+	const unsigned repmask = DEP_REP == 1 ? FULL : 0x55555555u << (lane & 1);   /* the lanes of my replica */
 
 	__shared__ int scratch[MAX_WPC][18];
 
@@ -1131,7 +1141,6 @@ k_deposit(const __grid_constant__ DepositSet set, Geom g, int nb,
 				}
 			}
 
-			int key = -1 - lane;          /* unique key for idle lanes */
 			int cell = 0;
 			double a00 = 0, a01 = 0, a10 = 0, a11 = 0;
 			if(valid)
@@ -1141,32 +1150,49 @@ k_deposit(const __grid_constant__ DepositSet set, Geom g, int nb,
 				cic_weights(g, x, y, i0x, i0y, w00, w01, w10, w11);
 				a00 = MUL(w00, vq); a01 = MUL(w01, vq); a10 = MUL(w10, vq); a11 = MUL(w11, vq);
 				cell = ((i0y - cy0) << g.lBX) + (i0x - cx0);
-				key = cell * DEP_REP + lane % DEP_REP;
 			}
-			const unsigned peers = __match_any_sync(FULL, key);
-			const int rank = __popc(peers & lt);
-			const int rounds = __reduce_max_sync(FULL, valid ? rank + 1 : 0);
-			for(int r = 0; r < rounds; r++)
+			/* lanes of my replica that hold a particle of my cell: one ballot per bit of the cell
+			 * index (MATCH.ANY is an order of magnitude slower than the handful of votes) */
+			unsigned peers = __ballot_sync(FULL, valid) & repmask;
+			for(int k = 0; k < cbits; k++)
 			{
-				if(valid && rank == r)
-				{
-#if DEP_RECORDS
-					double2 *rec = (double2 *) (t + 4 * cell);       /* {w00, w01}, {w10, w11} sums of the cell */
-					double2 v0 = rec[0], v1 = rec[1];
-					v0.x = ADD(v0.x, a00); v0.y = ADD(v0.y, a01);
-					v1.x = ADD(v1.x, a10); v1.y = ADD(v1.y, a11);
-					rec[0] = v0;
-					rec[1] = v1;
-#else
-					const double v0 = t[cell], v1 = t[NC + cell], v2 = t[2 * NC + cell], v3 = t[3 * NC + cell];
-					t[cell] = ADD(v0, a00);
-					t[NC + cell] = ADD(v1, a01);
-					t[2 * NC + cell] = ADD(v2, a10);
-					t[3 * NC + cell] = ADD(v3, a11);
-#endif
-				}
-				__syncwarp();
+				const unsigned bk = __ballot_sync(FULL, (cell >> k) & 1);
+				peers &= ((cell >> k) & 1) ? bk : ~bk;
 			}
+			const bool lead = valid && (peers & lt) == 0;
+			const int members = __reduce_max_sync(FULL, valid ? __popc(peers) : 0);
+			/* the first lane of every group collects the others' contributions in lane order and
+			 * is the only one to touch the accumulators: one read-modify-write round per batch */
+			unsigned rest = lead ? peers & ~(1u << lane) : 0u;
+			for(int r = 1; r < members; r++)
+			{
+				const int src = rest ? __ffs((int) rest) - 1 : lane;
+				const double b00 = __shfl_sync(FULL, a00, src), b01 = __shfl_sync(FULL, a01, src);
+				const double b10 = __shfl_sync(FULL, a10, src), b11 = __shfl_sync(FULL, a11, src);
+				if(rest)
+				{
+					a00 = ADD(a00, b00); a01 = ADD(a01, b01); a10 = ADD(a10, b10); a11 = ADD(a11, b11);
+					rest &= rest - 1;
+				}
+			}
+			if(lead)
+			{
+#if DEP_RECORDS
+				double2 *rec = (double2 *) (t + 4 * cell);       /* {w00, w01}, {w10, w11} sums of the cell */
+				double2 v0 = rec[0], v1 = rec[1];
+				v0.x = ADD(v0.x, a00); v0.y = ADD(v0.y, a01);
+				v1.x = ADD(v1.x, a10); v1.y = ADD(v1.y, a11);
+				rec[0] = v0;
+				rec[1] = v1;
+#else
+				const double v0 = t[cell], v1 = t[NC + cell], v2 = t[2 * NC + cell], v3 = t[3 * NC + cell];
+				t[cell] = ADD(v0, a00);
+				t[NC + cell] = ADD(v1, a01);
+				t[2 * NC + cell] = ADD(v2, a10);
+				t[3 * NC + cell] = ADD(v3, a11);
+#endif
+			}
+			__syncwarp();
 		}
 	}
 
