@@ -47,7 +47,7 @@ def ncu_traffic(kernel="k_gather_push<2>", path=None):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the
     committed `ncu --set full` extract of the same workload (profiles/, config A, one GPU)."""
     import csv
-    path = path or os.path.join(ROOT, "profiles", "r1f_ncu_full_summary.csv")
+    path = path or os.path.join(ROOT, "profiles", "r1h_ncu_full_summary.csv")
     try:
         rows = list(csv.reader(open(path)))
         hdr = rows[0]
@@ -349,7 +349,8 @@ def main():
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": peak_src,
                 "traffic": ncu_traffic() if (world == 1 and args.workload == "A") else None,
-                "traffic_source": "profiles/r1f_ncu_full_summary.csv (bytes per launch, mean of the two species)",
+                "traffic_source": ("profiles/r1h_ncu_full_summary.csv (bytes per launch, mean of the two species)"
+                                   if (world == 1 and args.workload == "A") else None),
                 "algorithmic_bytes_per_particle": BYTES_GATHER_PUSH, "particles_per_launch": nps,
                 "avg_launch_ms": t_push,
                 "whole_step_frac": (n_rank * args.steps / (ms * 1e-3)) * (BYTES_GATHER_PUSH + BYTES_DEPOSIT) / 1e9 / peak,
@@ -363,9 +364,10 @@ def main():
             "k_gather_push<1> (push + exchange, 96 B/particle)": {"avg_launch_ms": staged["push_ms_per_launch"],
                                                                    "achieved": gb(96.0, staged["push_ms_per_launch"]),
                                                                    "frac": gb(96.0, staged["push_ms_per_launch"]) / peak},
-            "k_deposit (+stitch, 16 B/particle)": {"avg_launch_ms": t_dep / nspecies,
-                                                    "achieved": gb(16.0, t_dep / nspecies),
-                                                    "frac": gb(16.0, t_dep / nspecies) / peak}}
+            # one launch deposits every species: 16 B x all particles of the rank
+            "k_deposit (all species, + stitch; 16 B/particle)": {"avg_launch_ms": t_dep,
+                                                                  "achieved": gb(16.0 * nspecies, t_dep),
+                                                                  "frac": gb(16.0 * nspecies, t_dep) / peak}}
 
     # ---- e2e: the same K steps with the particle state living in pinned HOST memory: every step
     # uploads it, runs one sim_step through the C ABI, and reads back particles and the four grids
