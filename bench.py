@@ -216,6 +216,12 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    # stdout carries the one JSON line and nothing else: whatever the libraries print on the way
+    # (NCCL's version banner with NCCL_DEBUG=VERSION, for one) goes to stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -421,7 +427,10 @@ def main():
                            "l2": "particle state per GPU (%.0f MB) exceeds the 126 MB L2" % (n_rank * 48 / 1e6)},
                 "clocks": clk, "e2e": e2e, "gpu_launches": int(launches0),
                 "roofline": roofline, "cpu_baseline": cpu, "wall_s_timed_region": wall}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     sim.close()
     if world > 1:
         dist.destroy_process_group()
