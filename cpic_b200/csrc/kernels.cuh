@@ -23,17 +23,6 @@
 
 #define FULL 0xffffffffu
 
-/* Layout switches, off by default. Both were measured on B200 (config A, round 1) and change
- * nothing (E_INTERLEAVED: 0.2984 vs 0.2987 ms per step in the push kernels) or lose slightly
- * (DEP_RECORDS: 0.165 vs 0.157 ms in the deposit); they stay for the next round's profiling.
- * E_INTERLEAVED: the gather reads (E_x, E_y) pairs from one interleaved tile with 16-byte loads
- * DEP_RECORDS:   the deposit keeps the four corner sums of a cell in one 32-byte record */
-#ifndef E_INTERLEAVED
-#define E_INTERLEAVED 0
-#endif
-#ifndef DEP_RECORDS
-#define DEP_RECORDS 0
-#endif
 #ifndef MAX_WPC
 #define MAX_WPC 8
 #endif
@@ -247,8 +236,7 @@ k_phi_finish(const double *__restrict__ raw, double *__restrict__ phi, Geom g, d
  * [nx, SE) of the device E arrays (column nx+j repeats column j) so that a particle
  * block at the right edge can fetch its tile with one TMA box. */
 static __global__ void
-k_field_E(const double *__restrict__ phi, double *__restrict__ Ex, double *__restrict__ Ey,
-		double2 *__restrict__ Exy, Geom g)
+k_field_E(const double *__restrict__ phi, double *__restrict__ Ex, double *__restrict__ Ey, Geom g)
 {
 	int ix = blockIdx.x * blockDim.x + threadIdx.x;
 	int iy = blockIdx.y;              /* 0 .. ny */
@@ -262,18 +250,6 @@ k_field_E(const double *__restrict__ phi, double *__restrict__ Ex, double *__res
 	const double ex = (p[x0] - p[x1]) / dx2;
 	Ey[(size_t) iy * g.SE + ix] = ey;
 	Ex[(size_t) iy * g.SE + ix] = ex;
-#if E_INTERLEAVED
-	/* the copy the particle kernels fetch their tiles from: (E_x, E_y) side by side */
-	Exy[(size_t) iy * g.SE + ix] = make_double2(ex, ey);
-#endif
-}
-
-/* (E_x, E_y) pairs from the two separate arrays (after cpic_b200_set_field) */
-static __global__ void
-k_interleave_E(const double *__restrict__ Ex, const double *__restrict__ Ey, double2 *__restrict__ Exy, size_t n)
-{
-	const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
-	if(i < n) Exy[i] = make_double2(Ex[i], Ey[i]);
 }
 
 /* Second half of the deposition: adds, in a fixed order, the halo sums that the CTAs of
@@ -445,22 +421,6 @@ arrival_slot(const Arrivals &A, const SpeciesDev &sp, int f)
 	return arrival_slot(A, sp.roff, sp.rcap, f);
 }
 
-/* Both components at once from the interleaved tile: the same products and sums, in the
- * same order, as two tile_gather calls */
-__device__ __forceinline__ void
-tile_gather2(const double2 *t, int TW, int lx, int ly, double w00, double w01, double w10, double w11,
-		double &Ex, double &Ey)
-{
-	const double2 *p = t + ly * TW + lx;
-	const double2 e00 = p[0], e01 = p[TW], e10 = p[1], e11 = p[TW + 1];
-	double vx = MUL(w00, e00.x), vy = MUL(w00, e00.y);
-	vx = FMA(w01, e01.x, vx); vy = FMA(w01, e01.y, vy);
-	vx = FMA(w10, e10.x, vx); vy = FMA(w10, e10.y, vy);
-	vx = FMA(w11, e11.x, vx); vy = FMA(w11, e11.y, vy);
-	Ex = vx;
-	Ey = vy;
-}
-
 /* MODE 0: stage_plasma_E alone   (gather, store E per particle)
  * MODE 1: stage_plasma_r alone   (push from the stored per-particle E, then exchange)
  * MODE 2: both fused             (gather + push + exchange; E kept when pEx != NULL)
@@ -518,13 +478,8 @@ k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 		mbar_init(bar, 1);
 		uint32_t bytes = 2u * (uint32_t) (g.TH * g.TW) * 8u;
 		mbar_expect_tx(bar, bytes);
-#if E_INTERLEAVED
-		/* one box of (E_x, E_y) pairs: twice the columns of a plain tile (mapEx is the pair map) */
-		tma_load_2d(tEx, &mapEx, 2 * cx * g.WPC * g.BX, by * g.BY, bar);
-#else
 		tma_load_2d(tEx, &mapEx, cx * g.WPC * g.BX, by * g.BY, bar);
 		tma_load_2d(tEy, &mapEy, cx * g.WPC * g.BX, by * g.BY, bar);
-#endif
 	}
 
 	/* MODE 0 leaves the arrivals where they are (outbox `cur`); a push consumes the
@@ -674,12 +629,8 @@ k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 			int i0x, i0y;
 			double w00, w01, w10, w11;
 			cic_weights(g, x, y, i0x, i0y, w00, w01, w10, w11);
-#if E_INTERLEAVED
-			tile_gather2((const double2 *) tEx, g.TW, i0x - tx0, i0y - ty0, w00, w01, w10, w11, Ex, Ey);
-#else
 			Ex = tile_gather(tEx, g.TW, i0x - tx0, i0y - ty0, w00, w01, w10, w11);
 			Ey = tile_gather(tEy, g.TW, i0x - tx0, i0y - ty0, w00, w01, w10, w11);
-#endif
 			if(MODE == 0)
 			{
 				if(own) { sp.pEx[s] = Ex; sp.pEy[s] = Ey; }
@@ -1177,20 +1128,11 @@ k_deposit(const __grid_constant__ DepositSet set, Geom g, int nb,
 			}
 			if(lead)
 			{
-#if DEP_RECORDS
-				double2 *rec = (double2 *) (t + 4 * cell);       /* {w00, w01}, {w10, w11} sums of the cell */
-				double2 v0 = rec[0], v1 = rec[1];
-				v0.x = ADD(v0.x, a00); v0.y = ADD(v0.y, a01);
-				v1.x = ADD(v1.x, a10); v1.y = ADD(v1.y, a11);
-				rec[0] = v0;
-				rec[1] = v1;
-#else
 				const double v0 = t[cell], v1 = t[NC + cell], v2 = t[2 * NC + cell], v3 = t[3 * NC + cell];
 				t[cell] = ADD(v0, a00);
 				t[NC + cell] = ADD(v1, a01);
 				t[2 * NC + cell] = ADD(v2, a10);
 				t[3 * NC + cell] = ADD(v3, a11);
-#endif
 			}
 			__syncwarp();
 		}
@@ -1225,11 +1167,7 @@ k_deposit(const __grid_constant__ DepositSet set, Geom g, int nb,
 				const int corner = a * 2 + bb;
 #pragma unroll
 				for(int rep = 0; rep < DEP_REP; rep++)
-#if DEP_RECORDS
-					v = ADD(v, tw[rep * 4 * NC + 4 * cell + corner]);
-#else
 					v = ADD(v, tw[rep * 4 * NC + corner * NC + cell]);
-#endif
 			}
 		}
 		double *dst;

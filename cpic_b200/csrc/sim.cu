@@ -76,7 +76,6 @@ struct cpic_b200_sim {
 	int device;
 
 	double *rho, *phi, *phi_raw, *Ex, *Ey, *G;
-	double2 *Exy;            /* (E_x, E_y) pairs, the layout the particle kernels read */
 	cufftDoubleComplex *gk;
 	cufftHandle plan_fwd, plan_inv;
 	bool have_plans;
@@ -116,7 +115,7 @@ typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, vo
 		CUtensorMapFloatOOBfill);
 
 static int
-make_tensor_map(CUtensorMap *map, double *base, const Geom &g, int pairs)
+make_tensor_map(CUtensorMap *map, double *base, const Geom &g)
 {
 	static encode_fn encode = NULL;
 	if(!encode)
@@ -129,11 +128,9 @@ make_tensor_map(CUtensorMap *map, double *base, const Geom &g, int pairs)
 		encode = (encode_fn) fn;
 	}
 	/* dim 0 = columns (contiguous), dim 1 = rows */
-	/* pairs: the interleaved (E_x, E_y) array seen as doubles, twice as many columns */
-	const int m = pairs ? 2 : 1;
-	cuuint64_t dims[2] = { (cuuint64_t) m * g.SE, (cuuint64_t) (g.ny + 1) };
-	cuuint64_t strides[1] = { (cuuint64_t) m * g.SE * sizeof(double) };
-	cuuint32_t box[2] = { (cuuint32_t) (m * g.TW), (cuuint32_t) g.TH };
+	cuuint64_t dims[2] = { (cuuint64_t) g.SE, (cuuint64_t) (g.ny + 1) };
+	cuuint64_t strides[1] = { (cuuint64_t) g.SE * sizeof(double) };
+	cuuint32_t box[2] = { (cuuint32_t) g.TW, (cuuint32_t) g.TH };
 	cuuint32_t estr[2] = { 1, 1 };
 	CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, dims, strides, box, estr,
 			CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -260,8 +257,6 @@ cpic_b200_create(const cpic_b200_params_t *pp, cpic_b200_sim_t **out)
 	CKD(cudaMemset(s->phi_raw, 0, (size_t) g.ny * g.S * sizeof(double)));
 	CKD(cudaMemset(s->Ex, 0, (size_t) (g.ny + 1) * g.SE * sizeof(double)));
 	CKD(cudaMemset(s->Ey, 0, (size_t) (g.ny + 1) * g.SE * sizeof(double)));
-	CKD(cudaMalloc(&s->Exy, (size_t) (g.ny + 1) * g.SE * sizeof(double2)));
-	CKD(cudaMemset(s->Exy, 0, (size_t) (g.ny + 1) * g.SE * sizeof(double2)));
 	const int ncx = g.nbx / g.WPC;
 	CKD(cudaMalloc(&s->hb, (size_t) g.nby * g.nx * sizeof(double)));
 	CKD(cudaMalloc(&s->hr, (size_t) ncx * g.ny * sizeof(double)));
@@ -300,13 +295,8 @@ cpic_b200_create(const cpic_b200_params_t *pp, cpic_b200_sim_t **out)
 		s->have_plans = true;
 	}
 
-#if E_INTERLEAVED
-	int rc = make_tensor_map(&s->mapEx, (double *) s->Exy, g, 1);
-	if(!rc) rc = make_tensor_map(&s->mapEy, s->Ey, g, 0);
-#else
-	int rc = make_tensor_map(&s->mapEx, s->Ex, g, 0);
-	if(!rc) rc = make_tensor_map(&s->mapEy, s->Ey, g, 0);
-#endif
+	int rc = make_tensor_map(&s->mapEx, s->Ex, g);
+	if(!rc) rc = make_tensor_map(&s->mapEy, s->Ey, g);
 	if(rc) { cpic_b200_destroy(s); return rc; }
 
 	/* barrier + per-warp scratch + two E tiles + per-warp prefetch rings (sized for the
@@ -342,7 +332,7 @@ cpic_b200_destroy(cpic_b200_sim_t *s)
 	for(int i = 0; i < CPIC_B200_MAX_SPECIES; i++) free_species(s->sp[i]);
 	if(s->comm) comm_destroy(s->comm);
 	if(s->have_plans) { cufftDestroy(s->plan_fwd); cufftDestroy(s->plan_inv); }
-	cudaFree(s->rho); cudaFree(s->phi); cudaFree(s->phi_raw); cudaFree(s->Ex); cudaFree(s->Ey); cudaFree(s->Exy);
+	cudaFree(s->rho); cudaFree(s->phi); cudaFree(s->phi_raw); cudaFree(s->Ex); cudaFree(s->Ey);
 	cudaFree(s->G); cudaFree(s->gk); cudaFree(s->hb); cudaFree(s->hr); cudaFree(s->hc);
 	cudaFree(s->red); cudaFree(s->errflag); cudaFree(s->img); cudaFree(s->img_off);
 	if(s->h_err) cudaFreeHost(s->h_err);
@@ -847,7 +837,7 @@ cpic_b200_stage_field_E(cpic_b200_sim_t *s)
 	if((rc = check_launch(s))) return rc;
 	if(s->comm && (rc = comm_phi_halo(s->comm, s->phi, s->stream))) return rc;
 	dim3 gridE((g.SE + 127) / 128, g.ny + 1);
-	k_field_E<<<gridE, 128, 0, s->stream>>>(s->phi, s->Ex, s->Ey, s->Exy, g);
+	k_field_E<<<gridE, 128, 0, s->stream>>>(s->phi, s->Ex, s->Ey, g);
 	return check_launch(s);
 }
 
@@ -1222,12 +1212,6 @@ cpic_b200_set_field(cpic_b200_sim_t *s, int f, const double *host)
 		for(int c = g.nx; c < g.SE; c++)
 			CK(cudaMemcpy2DAsync(base + c, (size_t) ds * sizeof(double), host + (c - g.nx) % g.nx,
 						(size_t) st * sizeof(double), sizeof(double), (size_t) r, cudaMemcpyHostToDevice, s->stream));
-	}
-	if(f == CPIC_B200_EX || f == CPIC_B200_EY)
-	{
-		const size_t n = (size_t) (s->g.ny + 1) * s->g.SE;
-		k_interleave_E<<<(unsigned) ((n + 255) / 256), 256, 0, s->stream>>>(s->Ex, s->Ey, s->Exy, n);
-		CK(cudaGetLastError());
 	}
 	CK(cudaStreamSynchronize(s->stream));
 	return 0;

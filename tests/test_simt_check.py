@@ -28,6 +28,16 @@ def simt_build():
     return LIB
 
 
+@pytest.fixture(scope="module")
+def simt_build_alt():
+    """The compile-time alternatives of the kernels: 16-byte cp.async instead of TMA bulk copies for the
+    segment batches (OWN_BULK=0), one deposit launch per species (DEP_FUSED=0), a two-stage ring."""
+    r = subprocess.run(["make", "-C", SIMT, "B=_build_alt", "EXTRA=-DOWN_BULK=0 -DDEP_FUSED=0 -DPIPE_STAGES=2"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    return os.path.join(SIMT, "_build_alt", "libcpic_b200_simt.so")
+
+
 def run_under_interpreter(lib, args, timeout=900):
     env = dict(os.environ, CPIC_B200_LIB=lib, CPIC_B200_SIMT_CHECK="1")
     r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-p", "no:cacheprovider", "-m", "gpu"] + args,
@@ -64,6 +74,12 @@ def test_kernel_parity_suite_under_the_interpreter(simt_build):
     limit, ragged species, far movers, image round trip -- same oracle, same 1e-12."""
     out = run_under_interpreter(simt_build, ["tests/test_gpu_parity.py"])
     assert "36 passed" in out or int(out.strip().splitlines()[-1].split()[0]) >= 36, out[-500:]
+
+
+def test_alternative_kernel_paths_under_the_interpreter(simt_build_alt):
+    """The switches that are off in the shipped build keep passing the same parity suite."""
+    run_under_interpreter(simt_build_alt, ["tests/test_gpu_parity.py", "-k",
+                                           "first_10_steps or bitwise or far_movers or hot_beam or deposit"])
 
 
 def test_physics_under_the_interpreter(simt_build):
