@@ -12,6 +12,14 @@
 #include <unordered_map>
 #include <vector>
 
+#if defined(__SANITIZE_ADDRESS__)
+/* AddressSanitizer has to be told about every stack switch */
+#include <sanitizer/common_interface_defs.h>
+#define SIMT_ASAN 1
+#else
+#define SIMT_ASAN 0
+#endif
+
 #if !defined(__x86_64__)
 #error "simt-check's context switch is written for x86-64"
 #endif
@@ -92,10 +100,38 @@ static bool aborting;
 static char abort_msg[512];
 static cudaError_t last_error = cudaSuccess;
 
+#if SIMT_ASAN
+static const void *sched_stack_bottom;
+static size_t sched_stack_size;
+#endif
+
+/* fiber -> scheduler */
 static void
 to_scheduler()
 {
+#if SIMT_ASAN
+	void *fake = NULL;
+	Fiber *me = cur;
+	__sanitizer_start_switch_fiber(me->state == DONE ? NULL : &fake, sched_stack_bottom, sched_stack_size);
+	simt_switch(&me->sp, sched_sp);
+	__sanitizer_finish_switch_fiber(fake, &sched_stack_bottom, &sched_stack_size);
+#else
 	simt_switch(&cur->sp, sched_sp);
+#endif
+}
+
+/* scheduler -> fiber f */
+static void
+to_fiber(Fiber &f)
+{
+#if SIMT_ASAN
+	void *fake = NULL;
+	__sanitizer_start_switch_fiber(&fake, f.stack, STACK);
+	simt_switch(&sched_sp, f.sp);
+	__sanitizer_finish_switch_fiber(fake, NULL, NULL);
+#else
+	simt_switch(&sched_sp, f.sp);
+#endif
 }
 
 static void
@@ -394,6 +430,9 @@ fiber_exit()
 static void
 fiber_entry()
 {
+#if SIMT_ASAN
+	__sanitizer_finish_switch_fiber(NULL, &sched_stack_bottom, &sched_stack_size);
+#endif
 	(*body)();
 	fiber_exit();
 }
@@ -483,7 +522,7 @@ launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> &fn)
 						cur = &f;
 						tid = f.tid;
 						n_switches++;
-						simt_switch(&sched_sp, f.sp);
+						to_fiber(f);
 						if(f.state == DONE) done++;
 						progress = true;
 					}
