@@ -403,13 +403,41 @@ def main():
         if world > 1:
             dist.all_reduce(te_t, op=dist.ReduceOp.MAX)
         te = float(te_t.item())
-        L.cpic_b200_host_free(host)
         moved = n_rank * 48 + 8 * nspecies + 4 * nspecies * ((params.nx // 8) * (params.ny // world // 8))
         e2e = {"value": n_total * e_steps / te, "unit": UNIT, "h2d_bytes_per_step": int(moved),
                "d2h_bytes_per_step": int(moved + fbytes), "steps": e_steps,
                "note": "the whole particle state (x,y,ux,uy,uz,id of every particle) is uploaded from pinned host "
                        "memory before and downloaded after every sim_step, plus the four grids: the worst case of "
                        "the drop-in (host-owned particle lists); a resident run only reads the grids back"}
+        # the two ways the drop-in binding (dropin/cpic_b200_stages.c) really runs, for comparison: the state
+        # stays on the device, and after every step the host copies are refreshed -- particles and grids
+        # ("eager", the default) or the grids only (CPIC_B200_SYNC=lazy). `value` above stays the strict one.
+        try:
+            if world > 1:
+                raise RuntimeError("measured on one GPU only")
+            def timed(with_particles):
+                barrier()
+                t1 = time.perf_counter()
+                for _ in range(e_steps):
+                    sim.step()
+                    if with_particles:
+                        L.cpic_b200_image_download(sim.h, host, nbytes)
+                    for k, a in fields.items():
+                        L.cpic_b200_get_field(sim.h, {"rho": 0, "phi": 1, "Ex": 2, "Ey": 3}[k], a.ctypes.data_as(C.c_void_p))
+                sim.sync()
+                barrier()
+                tt = torch.tensor([time.perf_counter() - t1], dtype=torch.float64, device="cuda")
+                if world > 1:
+                    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                return n_total * e_steps / float(tt.item())
+            e2e["dropin_modes"] = {
+                "eager (device-resident state; particles + grids read back every step)":
+                    {"value": timed(True), "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(moved + fbytes)},
+                "lazy (device-resident state; grids read back every step)":
+                    {"value": timed(False), "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(fbytes)}}
+        except Exception as exc:      # the extra modes must never cost the line
+            e2e["dropin_modes"] = {"error": repr(exc)}
+        L.cpic_b200_host_free(host)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
