@@ -23,6 +23,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 /* ---- the part of nccl.h that is used (stable ABI since NCCL 2.7) ---- */
@@ -256,14 +257,39 @@ struct FaceLayout {
 	int na;                  /* doubles per slot: OREC, + 2 with the field */
 };
 
-/* dir 0: row 0, codes 0,1,2 (to the north rank); dir 1: last row, codes 6,7,8 (south).
- * pack != 0: regions -> buffer; else buffer -> ghost rows (north buffer received from the
- * south rank fills the south ghost row and vice versa). */
+/* What one launch moves: every species, both faces. Grid: (blocks, 2 * species); the last CTA
+ * of a grid row handles the far-mover section of its (species, face). */
+struct FaceJob {
+	SpeciesSet set;
+	FaceLayout L[SET_MAX_SPECIES][2];     /* [species][0: codes 0,1,2 | 1: codes 6,7,8] */
+	unsigned long long off[SET_MAX_SPECIES + 1];   /* first double of a species' section in a face buffer */
+	int nbx;
+	int first_block[2];      /* of the block row whose regions are copied, per face */
+	double *buf[2];          /* face buffers: pack [to north, to south]; unpack [from south, from north] */
+	int pack;
+};
+
+static_assert(sizeof(FaceJob) <= 4096, "kernel parameters beyond the classic 4 KB limit");
+
+/* pack != 0: the regions of row 0 with codes 0,1,2 (to the north rank) and of the last row with
+ * codes 6,7,8 (south) -> buffers; else buffers -> ghost rows (what the south rank sent north
+ * fills the south ghost row and vice versa). */
 static __global__ void __launch_bounds__(256)
-k_face_copy(SpeciesDev sp, int arr, int nbx, int first_block, int code0, FaceLayout L,
-		double *__restrict__ buf, int pack)
+k_faces(const __grid_constant__ FaceJob job, int *__restrict__ errflag)
 {
-	const Outbox &ob = sp.ob[arr];
+	const int is = blockIdx.y >> 1, dir = blockIdx.y & 1;
+	const SpeciesDev &sp = job.set.sp[is];
+	const FaceLayout &L = job.L[is][dir];
+	const int nbx = job.nbx, first_block = job.first_block[dir], code0 = dir ? 6 : 0;
+	double *__restrict__ buf = job.buf[dir] + job.off[is];
+	if(blockIdx.x == gridDim.x - 1)
+	{
+		/* unpack: the list received on face `dir` came from the opposite direction's sender; it is
+		 * appended to the local far-mover list whatever its origin */
+		far_face(sp, dir, job.buf[dir] + job.off[is + 1] - FAR_SECTION, job.pack, errflag);
+		return;
+	}
+	const Outbox &ob = sp.ob[job.set.arr[is]];
 	const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
 	if(i < L.total)
 	{
@@ -273,7 +299,7 @@ k_face_copy(SpeciesDev sp, int arr, int nbx, int first_block, int code0, FaceLay
 		const size_t slot0 = (size_t) sp.roff[c] + (size_t) first_block * (size_t) sp.rcap[c];
 		const size_t r = i - L.off[k];
 		double *p = r < slots * OREC ? ob.rec + slot0 * OREC + r : ob.recE + slot0 * 2 + (r - slots * OREC);
-		if(pack) buf[i] = *p;
+		if(job.pack) buf[i] = *p;
 		else *p = buf[i];
 	}
 	else if(i < L.total + 3u * nbx)
@@ -282,7 +308,7 @@ k_face_copy(SpeciesDev sp, int arr, int nbx, int first_block, int code0, FaceLay
 		const int k = r / nbx, bx = r % nbx;
 		int *cnt = ob.count + (size_t) (code0 + k) * sp.nob + first_block + bx;
 		int *bc = (int *) (buf + L.total) + r;
-		if(pack) *bc = *cnt;
+		if(job.pack) *bc = *cnt;
 		else *cnt = *bc;
 	}
 }
@@ -305,9 +331,9 @@ face_layout(const SpeciesDev *sp, int nbx, int code0)
 /* The Y pass of comm_plasma between ranks (reference src/comm_plasma.c:1039-1120), all
  * species at once. Row 0's regions with codes 0,1,2 (moving north) land in the north rank's
  * south ghost row; the last row's regions with codes 6,7,8 in the south rank's north ghost
- * row. One message per face: small kernels gather every species' regions and counts into a
- * contiguous buffer, one NCCL group moves both faces, and the mirror kernels scatter them
- * into the ghost rows. */
+ * row. One message per face: one kernel gathers every species' regions, counts and far movers
+ * into the two face buffers, one NCCL group moves both faces, and the same kernel scatters
+ * what arrived into the ghost rows. */
 int
 comm_particles(Comm *c, SpeciesDev *const *sps, const int *arrs, int nsp, const Geom &g, int nb,
 		cudaStream_t stream, int *errflag, long long *launches)
@@ -332,15 +358,26 @@ comm_particles(Comm *c, SpeciesDev *const *sps, const int *arrs, int nsp, const 
 		for(int k = 0; k < 4; k++) CCK(cudaMalloc(&c->face[k], c->face_cap * sizeof(double)));
 	}
 	double *send_n = c->face[0], *send_s = c->face[1], *recv_s = c->face[2], *recv_n = c->face[3];
+	FaceJob job;
+	unsigned most = 0;
+	job.set.n = nsp;
 	for(int i = 0; i < nsp; i++)
 	{
-		const unsigned threads = Ln[i].total + 3u * nbx;
-		const int blocks = (int) ((threads + 255) / 256);
-		k_face_copy<<<blocks, 256, 0, stream>>>(*sps[i], arrs[i], nbx, 0, 0, Ln[i], send_n + off[i], 1);
-		k_face_copy<<<blocks, 256, 0, stream>>>(*sps[i], arrs[i], nbx, nb - nbx, 6, Ls[i], send_s + off[i], 1);
-		k_far_face<<<1, 256, 0, stream>>>(*sps[i], 0, send_n + off[i + 1] - FAR_SECTION, 1, errflag);
-		k_far_face<<<1, 256, 0, stream>>>(*sps[i], 1, send_s + off[i + 1] - FAR_SECTION, 1, errflag);
+		job.set.sp[i] = *sps[i];
+		job.set.arr[i] = arrs[i];
+		job.L[i][0] = Ln[i];
+		job.L[i][1] = Ls[i];
+		job.off[i] = off[i];
+		most = std::max(most, Ln[i].total + 3u * nbx);
 	}
+	job.off[nsp] = off[nsp];
+	job.nbx = nbx;
+	const dim3 grid((most + 255) / 256 + 1, 2 * nsp);
+	/* one launch gathers every species' regions, counts and far movers of both faces */
+	job.first_block[0] = 0; job.first_block[1] = nb - nbx;
+	job.buf[0] = send_n; job.buf[1] = send_s;
+	job.pack = 1;
+	k_faces<<<grid, 256, 0, stream>>>(job, errflag);
 	NCK(g_nccl.GroupStart());
 	NCK(g_nccl.Send(send_n, doubles, ncclFloat64, north, c->nc, stream));
 	NCK(g_nccl.Send(send_s, doubles, ncclFloat64, south, c->nc, stream));
@@ -348,17 +385,12 @@ comm_particles(Comm *c, SpeciesDev *const *sps, const int *arrs, int nsp, const 
 	NCK(g_nccl.Recv(recv_n, doubles, ncclFloat64, north, c->nc, stream));
 	NCK(g_nccl.GroupEnd());
 	/* what the south rank sent north (codes 0,1,2) fills our south ghost row, and vice versa */
-	for(int i = 0; i < nsp; i++)
-	{
-		const unsigned threads = Ln[i].total + 3u * nbx;
-		const int blocks = (int) ((threads + 255) / 256);
-		k_face_copy<<<blocks, 256, 0, stream>>>(*sps[i], arrs[i], nbx, nb + nbx, 0, Ln[i], recv_s + off[i], 0);
-		k_face_copy<<<blocks, 256, 0, stream>>>(*sps[i], arrs[i], nbx, nb, 6, Ls[i], recv_n + off[i], 0);
-		k_far_face<<<1, 256, 0, stream>>>(*sps[i], 0, recv_s + off[i + 1] - FAR_SECTION, 0, errflag);
-		k_far_face<<<1, 256, 0, stream>>>(*sps[i], 1, recv_n + off[i + 1] - FAR_SECTION, 0, errflag);
-	}
+	job.first_block[0] = nb + nbx; job.first_block[1] = nb;
+	job.buf[0] = recv_s; job.buf[1] = recv_n;
+	job.pack = 0;
+	k_faces<<<grid, 256, 0, stream>>>(job, errflag);
 	CCK(cudaGetLastError());
-	if(launches) *launches += 8 * nsp;
+	if(launches) *launches += 2;
 	return 0;
 }
 

@@ -77,6 +77,14 @@ struct SpeciesDev {
 	int *rfcount;            /* [2] */
 };
 
+/* Every species of a simulation, for the kernels that take one CTA (or grid row) per species */
+#define SET_MAX_SPECIES 8
+struct SpeciesSet {
+	SpeciesDev sp[SET_MAX_SPECIES];
+	int arr[SET_MAX_SPECIES];    /* the outbox that holds the pending arrivals */
+	int n;
+};
+
 #define FAR_CAP 65536
 #define FAR_FACE 2048
 
@@ -793,10 +801,11 @@ bitonic_sort(K *key, I *idx, int m)
 }
 
 static __global__ void __launch_bounds__(1024)
-k_far_insert(SpeciesDev sp, Geom g, int *__restrict__ errflag)
+k_far_insert(const __grid_constant__ SpeciesSet set, Geom g, int *__restrict__ errflag)
 {
 	__shared__ long long skey[FAR_SMEM];
 	__shared__ int sidx[FAR_SMEM];
+	const SpeciesDev &sp = set.sp[blockIdx.x];       /* one CTA per species */
 	int n = *sp.fcount;
 	if(n == 0) return;
 	if(n > FAR_CAP) n = FAR_CAP;
@@ -882,8 +891,8 @@ k_far_insert(SpeciesDev sp, Geom g, int *__restrict__ errflag)
  * face buffer section `buf` ([count as double][8 x FAR_FACE values]) and is emptied; else the
  * section received from a neighbour is appended to the local far-mover list, which the next
  * k_far_insert places. */
-static __global__ void __launch_bounds__(256)
-k_far_face(SpeciesDev sp, int dir, double *__restrict__ buf, int pack, int *__restrict__ errflag)
+__device__ __forceinline__ void
+far_face(const SpeciesDev &sp, int dir, double *__restrict__ buf, int pack, int *__restrict__ errflag)
 {
 	__shared__ int base;
 	if(pack)

@@ -908,29 +908,32 @@ static int
 exchange(sim_t_ *s)
 {
 	StageTimer t(s, T_EXCHANGE);
+	static_assert(SET_MAX_SPECIES >= CPIC_B200_MAX_SPECIES, "species set too small");
 	SpeciesDev *sps[CPIC_B200_MAX_SPECIES];
 	int arrs[CPIC_B200_MAX_SPECIES], nsp = 0;
+	SpeciesSet set;
 	for(int is = 0; is < s->p.nspecies; is++)
 	{
 		SpeciesHost &h = s->sp[is];
 		if(!h.block) continue;
-		/* particles that jumped further than a neighbouring block (normally none) */
-		k_far_insert<<<1, 1024, 0, s->stream>>>(h.d, s->g, s->errflag);
-		int rc = check_launch(s);
-		if(rc) return rc;
+		set.sp[nsp] = h.d;
+		set.arr[nsp] = h.arr;
 		sps[nsp] = &h.d;
 		arrs[nsp++] = h.arr;
 	}
-	if(s->comm && nsp)
+	set.n = nsp;
+	if(!nsp) return 0;
+	/* particles that jumped further than a neighbouring block (normally none): one CTA per species */
+	k_far_insert<<<nsp, 1024, 0, s->stream>>>(set, s->g, s->errflag);
+	int rc = check_launch(s);
+	if(rc) return rc;
+	if(s->comm)
 	{
-		int rc = comm_particles(s->comm, sps, arrs, nsp, s->g, s->nb, s->stream, s->errflag, &s->launches);
+		rc = comm_particles(s->comm, sps, arrs, nsp, s->g, s->nb, s->stream, s->errflag, &s->launches);
 		if(rc) return rc;
 		/* far movers received from the neighbour ranks */
-		for(int i = 0; i < nsp; i++)
-		{
-			k_far_insert<<<1, 1024, 0, s->stream>>>(*sps[i], s->g, s->errflag);
-			if((rc = check_launch(s))) return rc;
-		}
+		k_far_insert<<<nsp, 1024, 0, s->stream>>>(set, s->g, s->errflag);
+		if((rc = check_launch(s))) return rc;
 	}
 	return 0;
 }
