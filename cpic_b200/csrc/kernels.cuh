@@ -33,6 +33,33 @@
 #define OWN_BULK 1
 #endif
 
+/* SEG_AOSOA 0: a species' segments are six arrays (x y ux uy uz id) of nb*cap slots each.
+ * 1: batch-major -- the 32 slots of a batch hold x[32] y[32] ux[32] uy[32] uz[32] id[32] in
+ * 1536 contiguous bytes, so that a batch is one TMA copy and one address; the six pointers of
+ * SpeciesDev then point 32 doubles apart into one array. Either way element i of block b is
+ * ptr[seg_slot(cap, b, i)]. (The optional per-particle E arrays stay plain: b*cap + i.) */
+#ifndef SEG_AOSOA
+#define SEG_AOSOA 0
+#endif
+
+/* doubles from a batch's x values to its y values (and so on): SEG_STEP = 32 batch-major;
+ * in the plain layout the arrays are SpeciesDev::astride apart */
+#if SEG_AOSOA
+#define SEG_STEP ((size_t) 32)
+#else
+#define SEG_STEP ((size_t) sp.astride)
+#endif
+
+__host__ __device__ __forceinline__ size_t
+seg_slot(int cap, int b, int i)
+{
+#if SEG_AOSOA
+	return ((size_t) b * cap + (size_t) (i & ~31)) * 6 + (size_t) (i & 31);
+#else
+	return (size_t) b * cap + (size_t) i;
+#endif
+}
+
 /* Outbox: the particles that left their block in one push, one region per block and
  * destination code (geom.h), so that the receiving block finds its arrivals as
  * contiguous runs. A slot is one 48-byte record (x y ux uy uz id): a leaver is written
@@ -518,10 +545,12 @@ k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 		const unsigned q_ = base + (bi) * 32 + (lane & 15) * 2; \
 		double *d_ = st0_ + lane * 2; \
 		const unsigned h_ = lane >> 4; \
-		cp_async16(d_, sp.x + (size_t) h_ * sp.astride + q_); \
+		/* array a of the batch starts a*SEG_STEP doubles after its x values */ \
+		const double *g_ = sp.x + seg_slot(sp.cap, b, (bi) * 32) + (lane & 15) * 2 + (size_t) h_ * SEG_STEP; \
+		cp_async16(d_, g_); \
 		if(MODE != 0) { \
-			cp_async16(d_ + 64, sp.x + (size_t) (2 + h_) * sp.astride + q_); \
-			if(h_ == 0 || (with_id)) cp_async16(d_ + 128, sp.x + (size_t) (4 + h_) * sp.astride + q_); \
+			cp_async16(d_ + 64, g_ + 2 * SEG_STEP); \
+			if(h_ == 0 || (with_id)) cp_async16(d_ + 128, g_ + 4 * SEG_STEP); \
 		} \
 		if(MODE == 1) cp_async16(d_ + 192, (h_ ? sp.pEy : sp.pEx) + q_); \
 		cp_async_commit(); \
@@ -533,9 +562,15 @@ k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 			uint64_t *mb_ = sbar + (bi) % PIPE_STAGES; \
 			const int na_ = (MODE == 0 ? 2 : 5) + ((MODE != 0 && (with_id)) ? 1 : 0) + (MODE == 1 ? 2 : 0); \
 			mbar_expect_tx(mb_, (uint32_t) na_ * 256u); \
-			tma_bulk_load(st0_ + 0 * 32, sp.x + q_, 256, mb_); tma_bulk_load(st0_ + 1 * 32, sp.y + q_, 256, mb_); \
-			if(MODE != 0) { tma_bulk_load(st0_ + 2 * 32, sp.ux + q_, 256, mb_); tma_bulk_load(st0_ + 3 * 32, sp.uy + q_, 256, mb_); \
-				tma_bulk_load(st0_ + 4 * 32, sp.uz + q_, 256, mb_); if(with_id) tma_bulk_load(st0_ + 5 * 32, sp.id + q_, 256, mb_); } \
+			const size_t g_ = seg_slot(sp.cap, b, (bi) * 32); \
+			if(SEG_AOSOA) { \
+				/* the batch's arrays are contiguous: one copy */ \
+				tma_bulk_load(st0_, sp.x + g_, (MODE == 0 ? 2u : (with_id) ? 6u : 5u) * 256u, mb_); \
+			} else { \
+			tma_bulk_load(st0_ + 0 * 32, sp.x + g_, 256, mb_); tma_bulk_load(st0_ + 1 * 32, sp.y + g_, 256, mb_); \
+			if(MODE != 0) { tma_bulk_load(st0_ + 2 * 32, sp.ux + g_, 256, mb_); tma_bulk_load(st0_ + 3 * 32, sp.uy + g_, 256, mb_); \
+				tma_bulk_load(st0_ + 4 * 32, sp.uz + g_, 256, mb_); if(with_id) tma_bulk_load(st0_ + 5 * 32, sp.id + g_, 256, mb_); } \
+			} \
 			if(MODE == 1) { tma_bulk_load(st0_ + 6 * 32, sp.pEx + q_, 256, mb_); tma_bulk_load(st0_ + 7 * 32, sp.pEy + q_, 256, mb_); } \
 		} \
 	} else { \
@@ -682,7 +717,7 @@ k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 		const int dpos = w + __popc(ms & lt);
 		/* the id (and the kept E) only move when the particle changes slot */
 		const bool moved = !own || dpos != t;
-		if(!have_id && valid && (moved || leave)) pid = sp.id[s];      /* late fetch: first shifted batch only */
+		if(!have_id && valid && (moved || leave)) pid = sp.id[seg_slot(sp.cap, b, t)];      /* late fetch: first shifted batch only (segment) */
 		__syncwarp();                /* every id is read before a neighbour lane may overwrite its slot */
 
 		if(stay)
@@ -690,9 +725,10 @@ k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 			if(dpos < sp.cap)
 			{
 				const unsigned d = base + dpos;
-				if(pp.set_r || moved) { sp.x[d] = x; sp.y[d] = y; }
-				sp.ux[d] = ux; sp.uy[d] = uy; sp.uz[d] = uz;
-				if(moved) sp.id[d] = pid;
+				const size_t ds = seg_slot(sp.cap, b, dpos);
+				if(pp.set_r || moved) { sp.x[ds] = x; sp.y[ds] = y; }
+				sp.ux[ds] = ux; sp.uy[ds] = uy; sp.uz[ds] = uz;
+				if(moved) sp.id[ds] = pid;
 				if(sp.pEx) { sp.pEx[d] = Ex; sp.pEy[d] = Ey; }
 			}
 			else bad |= 2;
@@ -852,10 +888,10 @@ k_far_insert(const __grid_constant__ SpeciesSet set, Geom g, int *__restrict__ e
 		{
 			if(pos >= sp.cap) { atomicOr(errflag, ERRBIT_ABSORB); break; }
 			const int e = idx[j];
-			const size_t d = (size_t) b * sp.cap + pos;
-			sp.x[d] = sp.fx[e]; sp.y[d] = sp.fy[e];
-			sp.ux[d] = sp.fux[e]; sp.uy[d] = sp.fuy[e]; sp.uz[d] = sp.fuz[e];
-			sp.id[d] = sp.fid[e];
+			const size_t d = (size_t) b * sp.cap + pos, ds = seg_slot(sp.cap, b, pos);
+			sp.x[ds] = sp.fx[e]; sp.y[ds] = sp.fy[e];
+			sp.ux[ds] = sp.fux[e]; sp.uy[ds] = sp.fuy[e]; sp.uz[ds] = sp.fuz[e];
+			sp.id[ds] = sp.fid[e];
 			if(sp.pEx) { sp.pEx[d] = sp.fEx[e]; sp.pEy[d] = sp.fEy[e]; }
 			pos++;
 		}
@@ -940,21 +976,22 @@ k_regrow(SpeciesDev sp, SpeciesDev dst, Geom g, int nb, int arr)
 	{
 		const size_t d = dbase + i;
 		if(i >= dst.cap) break;
+		const size_t dd = seg_slot(dst.cap, b, i);
 		if(i < cnt)
 		{
-			const size_t s = base + i;
-			dst.x[d] = sp.x[s]; dst.y[d] = sp.y[s];
-			dst.ux[d] = sp.ux[s]; dst.uy[d] = sp.uy[s]; dst.uz[d] = sp.uz[s];
-			dst.id[d] = sp.id[s];
+			const size_t s = base + i, ss = seg_slot(sp.cap, b, i);
+			dst.x[dd] = sp.x[ss]; dst.y[dd] = sp.y[ss];
+			dst.ux[dd] = sp.ux[ss]; dst.uy[dd] = sp.uy[ss]; dst.uz[dd] = sp.uz[ss];
+			dst.id[dd] = sp.id[ss];
 			if(dst.pEx && sp.pEx) { dst.pEx[d] = sp.pEx[s]; dst.pEy[d] = sp.pEy[s]; }
 		}
 		else
 		{
 			const size_t s = arrival_slot(A, sp, i - cnt);
 			const double *r = in.rec + s * OREC;
-			dst.x[d] = r[0]; dst.y[d] = r[1];
-			dst.ux[d] = r[2]; dst.uy[d] = r[3]; dst.uz[d] = r[4];
-			dst.id[d] = __double_as_longlong(r[5]);
+			dst.x[dd] = r[0]; dst.y[dd] = r[1];
+			dst.ux[dd] = r[2]; dst.uy[dd] = r[3]; dst.uz[dd] = r[4];
+			dst.id[dd] = __double_as_longlong(r[5]);
 			if(dst.pEx && in.recE) { dst.pEx[d] = in.recE[s * 2]; dst.pEy[d] = in.recE[s * 2 + 1]; }
 		}
 	}
@@ -983,11 +1020,11 @@ k_absorb(SpeciesDev sp, Geom g, int nb, int arr, int *__restrict__ errflag)
 	}
 	for(int f = lane; f < A.total; f += 32)
 	{
-		const size_t so = arrival_slot(A, sp, f), d = base + cnt + f;
+		const size_t so = arrival_slot(A, sp, f), d = base + cnt + f, ds = seg_slot(sp.cap, b, cnt + f);
 		const double *r = in.rec + so * OREC;
-		sp.x[d] = r[0]; sp.y[d] = r[1];
-		sp.ux[d] = r[2]; sp.uy[d] = r[3]; sp.uz[d] = r[4];
-		sp.id[d] = __double_as_longlong(r[5]);
+		sp.x[ds] = r[0]; sp.y[ds] = r[1];
+		sp.ux[ds] = r[2]; sp.uy[ds] = r[3]; sp.uz[ds] = r[4];
+		sp.id[ds] = __double_as_longlong(r[5]);
 		if(sp.pEx) { sp.pEx[d] = in.recE[so * 2]; sp.pEy[d] = in.recE[so * 2 + 1]; }
 	}
 	__syncwarp();                /* every lane has read the old count */
@@ -1073,12 +1110,11 @@ k_deposit(const __grid_constant__ DepositSet set, Geom g, int nb,
 		const Arrivals A = find_arrivals(sp.acount, sp.nob, g, nb, b, lane, scratch[warp]);
 		const int cnt = sp.count[b];
 		const int T = cnt + A.total;
-		const size_t base = (size_t) b * sp.cap;
 
 		double px = 0, py = 0;
 		if(lane < T)
 		{
-			if(lane < cnt) { px = sx[base + lane]; py = sy[base + lane]; }
+			if(lane < cnt) { px = sx[seg_slot(sp.cap, b, lane)]; py = sy[seg_slot(sp.cap, b, lane)]; }
 			else
 			{
 				const double2 v = *(const double2 *) (arec + (size_t) arrival_slot(A, sp.roff, sp.rcap, lane - cnt) * OREC);
@@ -1093,7 +1129,7 @@ k_deposit(const __grid_constant__ DepositSet set, Geom g, int nb,
 			const double x = px, y = py;
 			if(i + 32 < T)
 			{
-				if(i + 32 < cnt) { px = sx[base + i + 32]; py = sy[base + i + 32]; }
+				if(i + 32 < cnt) { px = sx[seg_slot(sp.cap, b, i + 32)]; py = sy[seg_slot(sp.cap, b, i + 32)]; }
 				else
 				{
 					const double2 v = *(const double2 *) (arec + (size_t) arrival_slot(A, sp.roff, sp.rcap, i + 32 - cnt) * OREC);
@@ -1202,14 +1238,13 @@ k_image_copy(SpeciesDev sp, int nb, const int *__restrict__ cnt, const long long
 	if(b >= nb) return;
 	const int c = cnt[b];
 	const long long o = off[b];
-	const size_t base = (size_t) b * sp.cap;
 	double *arr[6] = { sp.x, sp.y, sp.ux, sp.uy, sp.uz, (double *) sp.id };
 #pragma unroll
 	for(int a = 0; a < 6; a++)
 		for(int i = lane; i < c; i += 32)
 		{
-			if(pack) img[(size_t) a * n + o + i] = arr[a][base + i];
-			else arr[a][base + i] = img[(size_t) a * n + o + i];
+			if(pack) img[(size_t) a * n + o + i] = arr[a][seg_slot(sp.cap, b, i)];
+			else arr[a][seg_slot(sp.cap, b, i)] = img[(size_t) a * n + o + i];
 		}
 	if(!pack && lane == 0) sp.count[b] = c;
 }
@@ -1223,11 +1258,10 @@ k_kinetic(SpeciesDev sp, int nb, double *__restrict__ out)
 	const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
 	if(b >= nb) return;
 	const int cnt = sp.count[b];
-	const size_t base = (size_t) b * sp.cap;
 	double acc = 0.0;
 	for(int i = lane; i < cnt; i += 32)
 	{
-		double ux = sp.ux[base + i], uy = sp.uy[base + i];
+		double ux = sp.ux[seg_slot(sp.cap, b, i)], uy = sp.uy[seg_slot(sp.cap, b, i)];
 		acc += ux * ux + uy * uy;
 	}
 	for(int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(FULL, acc, o);
@@ -1294,7 +1328,6 @@ k_init_uniform(SpeciesDev sp, Geom g, int nb, long long n, long long id0, double
 	const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
 	if(b >= nb) return;
 	const long long cnt = n / nb + (b < n % nb ? 1 : 0);
-	const size_t base = (size_t) b * sp.cap;
 	const int bx = b % g.nbx, by = b / g.nbx;
 	for(long long k = lane; k < cnt; k += 32)
 	{
@@ -1309,12 +1342,13 @@ k_init_uniform(SpeciesDev sp, Geom g, int nb, long long n, long long id0, double
 			x = ((double) (bx * g.BX) + 0.5 * g.BX) * g.dx;
 			y = g.y0 + ((double) (by * g.BY) + 0.5 * g.BY) * g.dy;
 		}
-		sp.x[base + k] = x;
-		sp.y[base + k] = y;
-		sp.ux[base + k] = (2.0 * u01(s) - 1.0) * vx;
-		sp.uy[base + k] = (2.0 * u01(s) - 1.0) * vy;
-		sp.uz[base + k] = 0.0;
-		sp.id[base + k] = gid;
+		const size_t ds = seg_slot(sp.cap, b, (int) k);
+		sp.x[ds] = x;
+		sp.y[ds] = y;
+		sp.ux[ds] = (2.0 * u01(s) - 1.0) * vx;
+		sp.uy[ds] = (2.0 * u01(s) - 1.0) * vy;
+		sp.uz[ds] = 0.0;
+		sp.id[ds] = gid;
 	}
 	if(lane == 0) sp.count[b] = (int) cnt;
 }

@@ -365,12 +365,14 @@ alloc_species(sim_t_ *s, int is, int cap)
 	CK(cudaMalloc(&h.block, h.block_bytes));
 	CK(cudaMemsetAsync(h.block, 0, h.block_bytes, s->stream));
 	char *b = (char *) h.block;
-	h.d.x = (double *) (b + 0 * arr);
-	h.d.y = (double *) (b + 1 * arr);
-	h.d.ux = (double *) (b + 2 * arr);
-	h.d.uy = (double *) (b + 3 * arr);
-	h.d.uz = (double *) (b + 4 * arr);
-	h.d.id = (long long *) (b + 5 * arr);
+	/* plain layout: six arrays `arr` bytes apart; batch-major (SEG_AOSOA): 32 doubles apart */
+	const size_t step = SEG_AOSOA ? 32 * sizeof(double) : arr;
+	h.d.x = (double *) (b + 0 * step);
+	h.d.y = (double *) (b + 1 * step);
+	h.d.ux = (double *) (b + 2 * step);
+	h.d.uy = (double *) (b + 3 * step);
+	h.d.uz = (double *) (b + 4 * step);
+	h.d.id = (long long *) (b + 5 * step);
 	h.d.count = (int *) (b + 6 * arr);
 	h.d.cap = cap;
 	h.d.astride = (unsigned) (arr / sizeof(double));
@@ -494,24 +496,22 @@ cpic_b200_set_particles(cpic_b200_sim_t *s, int is, int64_t n, const int64_t *id
 	}
 	cap = h.d.cap;
 
-	const size_t nslot = (size_t) s->nb * cap;
-	std::vector<double> hx(nslot, 0.0), hy(nslot, 0.0), hux(nslot, 0.0), huy(nslot, 0.0), huz(nslot, 0.0);
-	std::vector<long long> hid(nslot, 0);
+	/* the host image of the six segment arrays, in the device's layout: array a starts astep[a]
+	 * doubles after x, element i of block b sits seg_slot() further */
+	const size_t seg_doubles = (h.block_bytes - align256((size_t) s->nob * sizeof(int))) / sizeof(double);
+	const size_t astep = ((char *) h.d.y - (char *) h.d.x) / sizeof(double);
+	std::vector<double> hseg(seg_doubles, 0.0);
 	std::vector<int> fill((size_t) s->nb, 0);
 	for(int64_t i = 0; i < n; i++)
 	{
 		int b = blk[(size_t) i];
-		size_t k = (size_t) b * cap + (size_t) fill[(size_t) b]++;
-		hx[k] = x[i]; hy[k] = y[i];
-		hux[k] = ux[i]; huy[k] = uy[i]; huz[k] = uz ? uz[i] : 0.0;
-		hid[k] = id ? id[i] : i;
+		const size_t k = seg_slot(cap, b, fill[(size_t) b]++);
+		hseg[k] = x[i]; hseg[k + astep] = y[i];
+		hseg[k + 2 * astep] = ux[i]; hseg[k + 3 * astep] = uy[i]; hseg[k + 4 * astep] = uz ? uz[i] : 0.0;
+		const long long pid = id ? id[i] : i;
+		memcpy(&hseg[k + 5 * astep], &pid, sizeof(pid));
 	}
-	CK(cudaMemcpyAsync(h.d.x, hx.data(), nslot * sizeof(double), cudaMemcpyHostToDevice, s->stream));
-	CK(cudaMemcpyAsync(h.d.y, hy.data(), nslot * sizeof(double), cudaMemcpyHostToDevice, s->stream));
-	CK(cudaMemcpyAsync(h.d.ux, hux.data(), nslot * sizeof(double), cudaMemcpyHostToDevice, s->stream));
-	CK(cudaMemcpyAsync(h.d.uy, huy.data(), nslot * sizeof(double), cudaMemcpyHostToDevice, s->stream));
-	CK(cudaMemcpyAsync(h.d.uz, huz.data(), nslot * sizeof(double), cudaMemcpyHostToDevice, s->stream));
-	CK(cudaMemcpyAsync(h.d.id, hid.data(), nslot * sizeof(long long), cudaMemcpyHostToDevice, s->stream));
+	CK(cudaMemcpyAsync(h.d.x, hseg.data(), seg_doubles * sizeof(double), cudaMemcpyHostToDevice, s->stream));
 	CK(cudaMemcpyAsync(h.d.count, cnt.data(), (size_t) s->nb * sizeof(int), cudaMemcpyHostToDevice, s->stream));
 	for(int k = 0; k < 2; k++) CK(cudaMemsetAsync(h.d.ob[k].count, 0, (size_t) s->nob * 9 * sizeof(int), s->stream));
 	CK(cudaStreamSynchronize(s->stream));
@@ -715,10 +715,23 @@ cpic_b200_get_particles(cpic_b200_sim_t *s, int is, int64_t capn, int64_t *id, d
 	if(n > capn) return n;
 
 	const size_t nslot = (size_t) s->nb * cap;
+	/* the six segment arrays in one copy (they are one allocation, in either layout) */
+	const size_t seg_doubles = (h.block_bytes - align256((size_t) s->nob * sizeof(int))) / sizeof(double);
+	const size_t astep = ((char *) h.d.y - (char *) h.d.x) / sizeof(double);
+	std::vector<double> seg(seg_doubles);
+	if(cudaMemcpy(seg.data(), h.d.x, seg_doubles * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess)
+	{ fail(CPIC_B200_ECUDA, "particle download failed"); return -1; }
+	double *outs[6] = { x, y, ux, uy, uz, (double *) id };
+	for(int a = 0; a < 6; a++)
+	{
+		if(!outs[a]) continue;
+		size_t k = 0;
+		for(int b = 0; b < s->nb; b++)
+			for(int i = 0; i < cnt[(size_t) b]; i++)
+				outs[a][k++] = seg[seg_slot(cap, b, i) + (size_t) a * astep];
+	}
 	std::vector<double> tmp(nslot);
-	struct { const void *src; double *dst; } arrs[] = {
-		{ h.d.x, x }, { h.d.y, y }, { h.d.ux, ux }, { h.d.uy, uy }, { h.d.uz, uz },
-		{ h.d.pEx, Ex }, { h.d.pEy, Ey }, { h.d.id, (double *) id } };
+	struct { const void *src; double *dst; } arrs[] = { { h.d.pEx, Ex }, { h.d.pEy, Ey } };
 	for(auto &a : arrs)
 	{
 		if(!a.dst) continue;
