@@ -38,6 +38,15 @@ def simt_build_alt():
     return os.path.join(SIMT, "_build_alt", "libcpic_b200_simt.so")
 
 
+@pytest.fixture(scope="module")
+def simt_build_batch_major():
+    """Batch-major segments (SEG_AOSOA=1): the 32 slots of a batch hold their six arrays in 1536
+    contiguous bytes -- prepared for measurement, off in the shipped build."""
+    r = subprocess.run(["make", "-C", SIMT, "B=_build_aosoa", "EXTRA=-DSEG_AOSOA=1"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    return os.path.join(SIMT, "_build_aosoa", "libcpic_b200_simt.so")
+
+
 def run_under_interpreter(lib, args, timeout=900):
     env = dict(os.environ, CPIC_B200_LIB=lib, CPIC_B200_SIMT_CHECK="1")
     r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-p", "no:cacheprovider", "-m", "gpu"] + args,
@@ -80,6 +89,11 @@ def test_alternative_kernel_paths_under_the_interpreter(simt_build_alt):
     """The switches that are off in the shipped build keep passing the same parity suite."""
     run_under_interpreter(simt_build_alt, ["tests/test_gpu_parity.py", "-k",
                                            "first_10_steps or bitwise or far_movers or hot_beam or deposit"])
+
+
+def test_batch_major_segments_under_the_interpreter(simt_build_batch_major):
+    run_under_interpreter(simt_build_batch_major, ["tests/test_gpu_parity.py", "-k",
+                                                   "first_10_steps or bitwise or far_movers or image_round_trip or ragged"])
 
 
 def test_physics_under_the_interpreter(simt_build):
