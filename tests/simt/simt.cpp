@@ -675,6 +675,43 @@ struct Plan {
 };
 static std::vector<Plan> plans;
 
+/* exp(sign * 2 pi i k / n) with the exact symmetries of the unit circle (the angle is reduced to
+ * the first octant before sin/cos are taken, in long double): w[n-k] is exactly conj(w[k]),
+ * w[n/2-k] exactly its mirror. Without them a point charge's potential is not symmetric to the
+ * last bit and the self force of a lone particle drifts (the reference's constant-speed test). */
+static cplx
+unit_root(long long k, long long n, int sign)
+{
+	k %= n;
+	if(k < 0) k += n;
+	const long long o = 8 * k / n;                     /* octant 0..7 */
+	const long double tau = 6.283185307179586476925286766559005768L;
+	long double c, s;
+	if(o % 2 == 0)
+	{
+		const long double a = tau * (long double) (8 * k - o * n) / (long double) (8 * n);
+		c = cosl(a); s = sinl(a);
+	}
+	else
+	{
+		const long double a = tau * (long double) ((o + 1) * n - 8 * k) / (long double) (8 * n);
+		c = sinl(a); s = cosl(a);                      /* mirrored at the octant's end */
+	}
+	double x, y;
+	switch(o)
+	{
+	case 0: x = (double) c; y = (double) s; break;
+	case 1: x = (double) c; y = (double) s; break;
+	case 2: x = -(double) s; y = (double) c; break;
+	case 3: x = -(double) s; y = (double) c; break;
+	case 4: x = -(double) c; y = -(double) s; break;
+	case 5: x = -(double) c; y = -(double) s; break;
+	case 6: x = (double) s; y = -(double) c; break;
+	default: x = (double) s; y = -(double) c; break;
+	}
+	return cplx(x, sign * y);
+}
+
 /* in place, unnormalised; sign -1 forward, +1 inverse */
 static void
 fft1(cplx *a, int n, int stride, int sign)
@@ -693,11 +730,7 @@ fft1(cplx *a, int n, int stride, int sign)
 		for(int len = 2; len <= n; len <<= 1)
 		{
 			std::vector<cplx> w(len / 2);
-			for(int k = 0; k < len / 2; k++)
-			{
-				const double ang = sign * 2.0 * M_PI * k / len;
-				w[k] = cplx(cos(ang), sin(ang));
-			}
+			for(int k = 0; k < len / 2; k++) w[k] = unit_root(k, len, sign);
 			for(int i = 0; i < n; i += len)
 				for(int k = 0; k < len / 2; k++)
 				{
@@ -713,11 +746,7 @@ fft1(cplx *a, int n, int stride, int sign)
 		for(int k = 0; k < n; k++)
 		{
 			cplx s = 0;
-			for(int j = 0; j < n; j++)
-			{
-				const double ang = sign * 2.0 * M_PI * (double) (((long long) j * k) % n) / n;
-				s += t[j] * cplx(cos(ang), sin(ang));
-			}
+			for(int j = 0; j < n; j++) s += t[j] * unit_root((long long) j * k, n, sign);
 			o[k] = s;
 		}
 		t.swap(o);

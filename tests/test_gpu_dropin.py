@@ -20,8 +20,13 @@ def run(binary, *args, timeout=600):
     path = os.path.join(REF, binary)
     if not os.path.exists(path):
         pytest.skip(f"{binary} not built (needs /root/reference at build time)")
+    env = dict(os.environ)
+    if env.get("CPIC_B200_SIMT_CHECK") == "1" and binary.startswith("dropin_"):
+        # CPU suite (tests/test_simt_check.py): the drivers' cpic_b200_* calls resolve to the build of the
+        # same sources that runs the kernels under the SIMT interpreter
+        env["LD_PRELOAD"] = env["CPIC_B200_LIB"]
     # the drivers open conf/<name>.conf relative to the working directory: the repo's confs
-    return subprocess.run([path, *args], cwd=ROOT, capture_output=True, text=True, timeout=timeout)
+    return subprocess.run([path, *args], cwd=ROOT, capture_output=True, text=True, timeout=timeout, env=env)
 
 
 def test_reference_cyclotron_driver():

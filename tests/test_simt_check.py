@@ -96,6 +96,15 @@ def test_batch_major_segments_under_the_interpreter(simt_build_batch_major):
                                                    "first_10_steps or bitwise or far_movers or image_round_trip or ragged"])
 
 
+def test_reference_drivers_through_the_dropin_under_the_interpreter(simt_build):
+    """The reference's own test/cyclotron.c and its `cpic -q <conf>` main with output enabled, linked to
+    dropin/cpic_b200_stages.c, with the C ABI served by the interpreted kernels (the 50000-cycle
+    constant-speed and the 1200-step harmonic drivers are left to the GPU run)."""
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "dropin_cpic")):
+        pytest.skip("drop-in drivers not built (needs /root/reference at build time)")
+    run_under_interpreter(simt_build, ["tests/test_gpu_dropin.py", "-k", "cyclotron or cli_and_output"])
+
+
 def test_physics_under_the_interpreter(simt_build):
     """Two-stream growth rate and energy history, constant speed and cyclotron orbits (the 1200-step
     harmonic golden trajectory is left to the GPU run: minutes of interpretation)."""
