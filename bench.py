@@ -2,7 +2,7 @@
 """Benchmark of the cpic hot path (BASELINE.json: particle-steps/s of the full step
 push+deposit+gather+solve, and the fraction of the HBM roofline).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload A|B|C]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload A|B|C|D|cyc]
 
 N = 1 runs BASELINE.json configs[1]: conf/2d-2species.conf (the reference's two-species
 block on a 1024x1024 grid, 1e7 particles), started from the reference's own initial
@@ -35,6 +35,8 @@ WORKLOADS = {
     "C": ("2d-2species.conf", 4096, 4096, 500_000_000),
     # BASELINE configs[2]: cyclotron physics at scale (one species, uniform B, 2048^2, 1e8 particles)
     "cyc": ("cyclotron-2048.conf", 2048, 2048, 100_000_000),
+    # SURVEY 8 config D (weak scaling at production density): 2048^2 cells and 2.5e8 particles per GPU
+    "D": ("2d-2species.conf", 2048, 2048, 125_000_000),
 }
 
 
@@ -353,7 +355,7 @@ def main():
     t_dep = stage_ms["field_rho"] / args.steps
     roofline = {"bound": "hbm", "kernel": "k_gather_push<2> (fused field gather + Boris push)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "peak_source": peak_src,
+                "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0,
                 "traffic": ncu_traffic() if (world == 1 and args.workload == "A") else None,
                 "traffic_source": ("profiles/r1h_ncu_full_summary.csv (bytes per launch, mean of the two species)"
                                    if (world == 1 and args.workload == "A") else None),
