@@ -59,6 +59,9 @@ EXPORTS = {
     "cpic_b200_set_particles": (_i, [_vp, _i, _i64] + [_vp] * 6),
     "cpic_b200_capacity": (_i64, [_vp, _i]),
     "cpic_b200_reserve": (_i, [_vp, _i, _i64]),
+    "cpic_b200_count_particles": (_i, [_vp, _i, _i64, _vp, _vp]),
+    "cpic_b200_reserve_counted": (_i, [_vp, _i]),
+    "cpic_b200_add_particles": (_i, [_vp, _i, _i64] + [_vp] * 6),
     "cpic_b200_occupancy": (_i, [_vp, _i, C.POINTER(_i64 * 6)]),
     "cpic_b200_num_particles": (_i64, [_vp, _i]),
     "cpic_b200_get_particles": (_i64, [_vp, _i, _i64] + [_vp] * 8),
@@ -91,6 +94,8 @@ EXPORTS = {
     "cpic_b200_conf_params": (_i, [_vp, _i, _i, _i, C.POINTER(ParamsC), C.POINTER(RunC)]),
     "cpic_b200_conf_init_particles": (_i, [_vp, _i] + [_pp] * 5),
     "cpic_b200_sim_from_conf": (_i, [C.c_char_p, _i, _i, _i, _i, _pp, C.POINTER(RunC)]),
+    "cpic_b200_sim_from_conf_streamed": (_i, [C.c_char_p, _i, _i, _i, _i, _i64, _pp, C.POINTER(RunC)]),
+    "cpic_b200_conf_stream_particles": (_i, [_vp, _i, _i64, _vp, _vp]),
     "cpic_b200_write_fields": (_i, [_vp, C.c_char_p, _i64, _i64, _i64, _i64, _d, _d]),
     "cpic_b200_main": (_i, [_i, C.POINTER(C.c_char_p)]),
 }

@@ -159,7 +159,13 @@ cpic_b200_main(int argc, char **argv)
 	cpic_b200_conf_free(conf);
 	if(!run.output_enabled) fprintf(stderr, "No output path specified, output will not be saved\n");
 	if(run.stop_SEM > 0.0) fprintf(stderr, "Sampling enabled with relative error limit %e\n", run.stop_SEM);
-	if(cpic_b200_sim_from_conf(fn, 0, 1, -1, 1, &sim, NULL))
+	/* populations beyond 2^27 particles are drawn and uploaded in batches: the host arrays of the
+	 * one-shot path would not fit next to the binning copies (1e9 particles = 48 GB each) */
+	long long total = 0;
+	for(int is = 0; is < p.nspecies; is++) total += run.nparticles[is];
+	const int rc_init = total > (1LL << 27) ? cpic_b200_sim_from_conf_streamed(fn, 0, 1, -1, 1, 1 << 24, &sim, NULL)
+			: cpic_b200_sim_from_conf(fn, 0, 1, -1, 1, &sim, NULL);
+	if(rc_init)
 	{
 		fprintf(stderr, "sim_init failed\n%s\n", cpic_b200_last_error());
 		return 1;

@@ -170,11 +170,11 @@ cpic_b200_conf_params(const cpic_b200_conf_t *c, int rank, int nranks, int devic
 }
 
 /* particles_init, reference src/particle.c:178-213, for every chunk of every reference
- * process, in the reference's loop order (src/plasma.c:292-316 -> :192-283 -> :17-128). */
-extern "C" int
-cpic_b200_conf_init_particles(const cpic_b200_conf_t *c, int ref_nprocs,
-		int64_t *const *id, double *const *x, double *const *y,
-		double *const *ux, double *const *uy)
+ * process, in the reference's loop order (src/plasma.c:292-316 -> :192-283 -> :17-128).
+ * `put(species, i, x, y, ux, uy)` receives every particle as it is drawn; a non-zero return stops. */
+template <typename Put>
+static int
+generate_particles(const cpic_b200_conf_t *c, int ref_nprocs, Put put)
 {
 	cpic_b200_params_t p;
 	cpic_b200_run_t run;
@@ -225,14 +225,14 @@ cpic_b200_conf_init_particles(const cpic_b200_conf_t *c, int ref_nprocs,
 				const Init &in = init[(size_t) is];
 				for(long long i = first; i < run.nparticles[is]; i += step)
 				{
-					id[is][i] = i;
+					double x, y, ux, uy;
 					if(in.method == 0)
 					{
 						/* src/particle.c:17-21, :69-73: rand() / (RAND_MAX + 1.0) * (b - a) + a */
-						x[is][i] = rand() / (RAND_MAX + 1.0) * (L[0] - 0.0) + 0.0;
-						y[is][i] = rand() / (RAND_MAX + 1.0) * (L[1] - 0.0) + 0.0;
-						ux[is][i] = rand() / (RAND_MAX + 1.0) * (in.v[0] - -in.v[0]) + -in.v[0];
-						uy[is][i] = rand() / (RAND_MAX + 1.0) * (in.v[1] - -in.v[1]) + -in.v[1];
+						x = rand() / (RAND_MAX + 1.0) * (L[0] - 0.0) + 0.0;
+						y = rand() / (RAND_MAX + 1.0) * (L[1] - 0.0) + 0.0;
+						ux = rand() / (RAND_MAX + 1.0) * (in.v[0] - -in.v[0]) + -in.v[0];
+						uy = rand() / (RAND_MAX + 1.0) * (in.v[1] - -in.v[1]) + -in.v[1];
 					}
 					else
 					{
@@ -245,13 +245,116 @@ cpic_b200_conf_init_particles(const cpic_b200_conf_t *c, int ref_nprocs,
 							r[d] = fmod(fma(in.dr[d], (double) i, in.r0[d]), L[d]);
 							if(r[d] < 0.0) r[d] += L[d];
 						}
-						x[is][i] = r[0]; y[is][i] = r[1];
-						ux[is][i] = in.v[0]; uy[is][i] = in.v[1];
+						x = r[0]; y = r[1];
+						ux = in.v[0]; uy = in.v[1];
 					}
+					if((rc = put(is, i, x, y, ux, uy))) return rc;
 				}
 			}
 		}
 	}
+	return 0;
+}
+
+extern "C" int
+cpic_b200_conf_init_particles(const cpic_b200_conf_t *c, int ref_nprocs,
+		int64_t *const *id, double *const *x, double *const *y,
+		double *const *ux, double *const *uy)
+{
+	return generate_particles(c, ref_nprocs, [&](int is, long long i, double px, double py, double pux, double puy) {
+		id[is][i] = i;
+		x[is][i] = px; y[is][i] = py;
+		ux[is][i] = pux; uy[is][i] = puy;
+		return 0;
+	});
+}
+
+extern "C" int
+cpic_b200_conf_stream_particles(const cpic_b200_conf_t *c, int ref_nprocs, int64_t batch,
+		cpic_b200_particle_sink_t sink, void *ctx)
+{
+	if(!sink || batch < 1) { front_set_error("stream_particles: no sink or empty batch"); return CPIC_B200_EINVAL; }
+	std::vector<int64_t> id; std::vector<double> x, y, ux, uy;
+	id.reserve((size_t) batch); x.reserve((size_t) batch); y.reserve((size_t) batch);
+	ux.reserve((size_t) batch); uy.reserve((size_t) batch);
+	int cur = -1;
+	auto flush = [&]() {
+		int rc = 0;
+		if(!id.empty()) rc = sink(ctx, cur, (int64_t) id.size(), id.data(), x.data(), y.data(), ux.data(), uy.data());
+		id.clear(); x.clear(); y.clear(); ux.clear(); uy.clear();
+		return rc;
+	};
+	int rc = generate_particles(c, ref_nprocs, [&](int is, long long i, double px, double py, double pux, double puy) {
+		if(is != cur || (int64_t) id.size() >= batch)
+		{
+			int r = flush();
+			if(r) return r;
+			cur = is;
+		}
+		id.push_back(i); x.push_back(px); y.push_back(py); ux.push_back(pux); uy.push_back(puy);
+		return 0;
+	});
+	if(!rc) rc = flush();
+	return rc;
+}
+
+/* The slab filter of particle_comm_initial (reference src/particle.h:19-20) over a batch */
+struct SlabSink {
+	cpic_b200_sim_t *sim;
+	double dy;
+	long long ny, rows, rank;
+	int pass;                /* 0: count, 1: add */
+	std::vector<int64_t> id; std::vector<double> x, y, ux, uy;
+};
+
+static int
+slab_sink(void *ctx, int is, int64_t n, const int64_t *id, const double *x, const double *y,
+		const double *ux, const double *uy)
+{
+	SlabSink &k = *(SlabSink *) ctx;
+	if(k.pass == 0) return cpic_b200_count_particles(k.sim, is, n, x, y);
+	k.id.clear(); k.x.clear(); k.y.clear(); k.ux.clear(); k.uy.clear();
+	for(int64_t i = 0; i < n; i++)
+	{
+		long long row = (long long) floor(y[i] * (1.0 / k.dy));
+		if(row < 0) row = 0;
+		if(row > k.ny - 1) row = k.ny - 1;
+		if(row / k.rows != k.rank) continue;
+		k.id.push_back(id[i]); k.x.push_back(x[i]); k.y.push_back(y[i]); k.ux.push_back(ux[i]); k.uy.push_back(uy[i]);
+	}
+	return cpic_b200_add_particles(k.sim, is, (int64_t) k.id.size(), k.id.data(), k.x.data(), k.y.data(),
+			k.ux.data(), k.uy.data(), NULL);
+}
+
+extern "C" int
+cpic_b200_sim_from_conf_streamed(const char *path, int rank, int nranks, int device, int ref_nprocs,
+		int64_t batch, cpic_b200_sim_t **out, cpic_b200_run_t *run)
+{
+	cpic_b200_conf_t *c = NULL;
+	cpic_b200_params_t p;
+	cpic_b200_run_t local;
+	if(!run) run = &local;
+	if(batch < 1) batch = 1 << 22;
+	int rc = cpic_b200_conf_load(path, &c);
+	if(rc) return rc;
+	rc = cpic_b200_conf_params(c, rank, nranks, device, &p, run);
+	cpic_b200_sim_t *sim = NULL;
+	if(!rc) rc = cpic_b200_create(&p, &sim);
+	if(rc) { cpic_b200_conf_free(c); return rc; }
+	SlabSink k;
+	k.sim = sim;
+	k.dy = p.Ly / (double) p.ny;
+	k.ny = p.ny; k.rows = p.ny / nranks; k.rank = rank;
+	/* the population is drawn twice from the same seed: once to size the blocks, once to fill them */
+	k.pass = 0;
+	rc = cpic_b200_conf_stream_particles(c, ref_nprocs, batch, slab_sink, &k);
+	for(int is = 0; is < p.nspecies && !rc; is++) rc = cpic_b200_reserve_counted(sim, is);
+	k.pass = 1;
+	if(!rc) rc = cpic_b200_conf_stream_particles(c, ref_nprocs, batch, slab_sink, &k);
+	cpic_b200_conf_free(c);
+	if(!rc && nranks == 1) rc = cpic_b200_pre_step(sim);
+	if(rc) { cpic_b200_destroy(sim); return rc; }
+	*out = sim;
 	return 0;
 }
 

@@ -1226,8 +1226,9 @@ k_deposit(const __grid_constant__ DepositSet set, Geom g, int nb,
 }
 
 /* Compact image of a species for host round trips: the live particles of every block, block
- * after block, without the slack of the segments. pack != 0: segments -> image, else
- * image -> segments. The image holds n values per array (x y ux uy uz id), `off` the
+ * after block, without the slack of the segments. pack 1: segments -> image; 0: image ->
+ * segments, replacing their content; -1: image appended to the segments (streamed
+ * initialisation). The image holds n values per array (x y ux uy uz id), `off` the
  * exclusive prefix of the block counts. One warp per block. */
 static __global__ void __launch_bounds__(256)
 k_image_copy(SpeciesDev sp, int nb, const int *__restrict__ cnt, const long long *__restrict__ off,
@@ -1238,15 +1239,17 @@ k_image_copy(SpeciesDev sp, int nb, const int *__restrict__ cnt, const long long
 	if(b >= nb) return;
 	const int c = cnt[b];
 	const long long o = off[b];
+	const int at = pack < 0 ? sp.count[b] : 0;       /* first slot written */
 	double *arr[6] = { sp.x, sp.y, sp.ux, sp.uy, sp.uz, (double *) sp.id };
 #pragma unroll
 	for(int a = 0; a < 6; a++)
 		for(int i = lane; i < c; i += 32)
 		{
-			if(pack) img[(size_t) a * n + o + i] = arr[a][seg_slot(sp.cap, b, i)];
-			else arr[a][seg_slot(sp.cap, b, i)] = img[(size_t) a * n + o + i];
+			if(pack > 0) img[(size_t) a * n + o + i] = arr[a][seg_slot(sp.cap, b, i)];
+			else arr[a][seg_slot(sp.cap, b, at + i)] = img[(size_t) a * n + o + i];
 		}
-	if(!pack && lane == 0) sp.count[b] = c;
+	__syncwarp();                /* every lane has read the old count */
+	if(pack <= 0 && lane == 0) sp.count[b] = at + c;
 }
 
 /* Kinetic energy per species: sum(ux^2 + uy^2), reference src/sim.c:366-395 (compiled

@@ -54,6 +54,7 @@ struct SpeciesHost {
 	void *oblock;            /* the two outboxes */
 	void *fblock;            /* far-mover list */
 	int reserve;             /* floor for the block capacity (cpic_b200_reserve) */
+	std::vector<int> *tally; /* per-block counts of a streamed initialisation (count_particles / add_particles) */
 	double *pE;              /* optional per-particle E (segment and outboxes) */
 	int arr;                 /* outbox that holds the pending arrivals */
 	long long n;
@@ -319,8 +320,9 @@ free_species(SpeciesHost &h)
 	cudaFree(h.pE);
 	double q = h.q, m = h.m;
 	int reserve = h.reserve;
+	std::vector<int> *tally = h.tally;
 	memset(&h, 0, sizeof(h));
-	h.q = q; h.m = m; h.reserve = reserve;
+	h.q = q; h.m = m; h.reserve = reserve; h.tally = tally;
 }
 
 extern "C" void
@@ -329,7 +331,12 @@ cpic_b200_destroy(cpic_b200_sim_t *s)
 	if(!s) return;
 	cudaSetDevice(s->device);
 	if(s->stream) cudaStreamSynchronize(s->stream);
-	for(int i = 0; i < CPIC_B200_MAX_SPECIES; i++) free_species(s->sp[i]);
+	for(int i = 0; i < CPIC_B200_MAX_SPECIES; i++)
+	{
+		free_species(s->sp[i]);
+		delete s->sp[i].tally;
+		s->sp[i].tally = NULL;
+	}
 	if(s->comm) comm_destroy(s->comm);
 	if(s->have_plans) { cufftDestroy(s->plan_fwd); cufftDestroy(s->plan_inv); }
 	cudaFree(s->rho); cudaFree(s->phi); cudaFree(s->phi_raw); cudaFree(s->Ex); cudaFree(s->Ey);
@@ -351,6 +358,7 @@ static size_t
 align256(size_t v) { return (v + 255) & ~(size_t) 255; }
 
 static int ensure_particle_E(sim_t_ *s, int is);
+static int image_staging(sim_t_ *s, size_t doubles);
 
 /* (Re)allocate one species with `cap` slots per block */
 static int
@@ -516,6 +524,112 @@ cpic_b200_set_particles(cpic_b200_sim_t *s, int is, int64_t n, const int64_t *id
 	for(int k = 0; k < 2; k++) CK(cudaMemsetAsync(h.d.ob[k].count, 0, (size_t) s->nob * 9 * sizeof(int), s->stream));
 	CK(cudaStreamSynchronize(s->stream));
 	h.n = n;
+	return 0;
+}
+
+/* Streamed initialisation for populations whose host arrays do not fit at once (1e9 particles,
+ * SURVEY 8d): the caller generates the population twice, batch by batch --
+ *   1. cpic_b200_count_particles(): per-block tallies, on the host;
+ *   2. cpic_b200_reserve_counted(): segments sized from the tallies;
+ *   3. cpic_b200_add_particles(): every batch is binned (stable) and appended to its blocks.
+ * Inside a block the particles end up in batch order, then input order. */
+extern "C" int
+cpic_b200_count_particles(cpic_b200_sim_t *s, int is, int64_t n, const double *x, const double *y)
+{
+	if(!s || is < 0 || is >= s->p.nspecies || n < 0 || (n && (!x || !y)))
+		return fail(CPIC_B200_EINVAL, "bad species or arrays");
+	SpeciesHost &h = s->sp[is];
+	const Geom &g = s->g;
+	/* tallies are kept for the blocks of every rank's slab: each rank sees the whole stream, so all
+	 * of them arrive at the same capacity without talking to each other */
+	if(!h.tally) h.tally = new std::vector<int>((size_t) g.nbx * (size_t) g.nby_glob, 0);
+	for(int64_t i = 0; i < n; i++)
+	{
+		if(!(x[i] >= 0.0 && x[i] <= g.Lx) || !(y[i] >= 0.0 && y[i] <= g.Ly))
+			return fail(CPIC_B200_EINVAL, "species %d: particle %lld at (%g, %g) lies outside the domain", is,
+					(long long) i, x[i], y[i]);
+		const size_t b = (size_t) (global_row(g, y[i]) >> g.lBY) * (size_t) g.nbx + (size_t) (cell_ix(g, x[i]) >> g.lBX);
+		(*h.tally)[b]++;
+	}
+	return 0;
+}
+
+extern "C" int
+cpic_b200_reserve_counted(cpic_b200_sim_t *s, int is)
+{
+	if(!s || is < 0 || is >= s->p.nspecies) return fail(CPIC_B200_EINVAL, "bad species");
+	CK(cudaSetDevice(s->device));
+	SpeciesHost &h = s->sp[is];
+	if(!h.tally) return fail(CPIC_B200_EINVAL, "species %d: cpic_b200_count_particles was not called", is);
+	long long total = 0;
+	int maxc = 0;
+	for(int c : *h.tally) { total += c; maxc = std::max(maxc, c); }
+	const long long nbg = (long long) h.tally->size();
+	const long long mean = nbg ? (total + nbg - 1) / nbg : 0;
+	int cap = cap_for(s, std::max<long long>(maxc, mean));
+	if(cap < h.reserve) cap = h.reserve;
+	delete h.tally;
+	h.tally = NULL;
+	int rc = alloc_species(s, is, cap);       /* zero counts, empty outboxes */
+	if(rc) return rc;
+	h.n = 0;
+	CK(cudaStreamSynchronize(s->stream));
+	return 0;
+}
+
+extern "C" int
+cpic_b200_add_particles(cpic_b200_sim_t *s, int is, int64_t n, const int64_t *id,
+		const double *x, const double *y, const double *ux, const double *uy, const double *uz)
+{
+	if(!s || is < 0 || is >= s->p.nspecies || n < 0 || (n && (!id || !x || !y || !ux || !uy)))
+		return fail(CPIC_B200_EINVAL, "bad species or arrays");
+	CK(cudaSetDevice(s->device));
+	SpeciesHost &h = s->sp[is];
+	if(!h.block) return fail(CPIC_B200_EINVAL, "species %d has no storage: reserve_counted or set_particles first", is);
+	if(n == 0) return 0;
+	const Geom &g = s->g;
+	/* stable binning of the batch, then the compact image the append kernel scatters */
+	std::vector<int> blk((size_t) n), cnt((size_t) s->nb, 0), have((size_t) s->nb);
+	for(int64_t i = 0; i < n; i++)
+	{
+		if(!(x[i] >= 0.0 && x[i] <= g.Lx) || !(y[i] >= g.y0 && y[i] <= g.y0 + g.dy * g.ny))
+			return fail(CPIC_B200_EINVAL, "species %d: particle %lld at (%g, %g) lies outside this rank's slab", is,
+					(long long) i, x[i], y[i]);
+		const int b = block_of(g, x[i], y[i]);
+		blk[(size_t) i] = b;
+		cnt[(size_t) b]++;
+	}
+	CK(cudaMemcpyAsync(have.data(), h.d.count, have.size() * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+	CK(cudaStreamSynchronize(s->stream));
+	std::vector<long long> off((size_t) s->nb);
+	long long m = 0;
+	for(int b = 0; b < s->nb; b++)
+	{
+		if(have[(size_t) b] + cnt[(size_t) b] > h.d.cap)
+			return fail(CPIC_B200_ECAPACITY, "species %d: block %d would hold %d particles, capacity %d", is, b,
+					have[(size_t) b] + cnt[(size_t) b], h.d.cap);
+		off[(size_t) b] = m;
+		m += cnt[(size_t) b];
+	}
+	std::vector<double> img((size_t) 6 * (size_t) n);
+	std::vector<long long> at(off);
+	for(int64_t i = 0; i < n; i++)
+	{
+		const size_t k = (size_t) at[(size_t) blk[(size_t) i]]++;
+		img[k] = x[i]; img[(size_t) n + k] = y[i];
+		img[2 * (size_t) n + k] = ux[i]; img[3 * (size_t) n + k] = uy[i]; img[4 * (size_t) n + k] = uz ? uz[i] : 0.0;
+		memcpy(&img[5 * (size_t) n + k], &id[i], sizeof(int64_t));
+	}
+	int rc = image_staging(s, (size_t) 6 * (size_t) n);
+	if(rc) return rc;
+	int *dcnt = (int *) (s->img_off + s->nb + 1);
+	CK(cudaMemcpyAsync(s->img_off, off.data(), off.size() * sizeof(long long), cudaMemcpyHostToDevice, s->stream));
+	CK(cudaMemcpyAsync(dcnt, cnt.data(), cnt.size() * sizeof(int), cudaMemcpyHostToDevice, s->stream));
+	CK(cudaMemcpyAsync(s->img, img.data(), img.size() * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+	k_image_copy<<<(s->nb + 7) / 8, 256, 0, s->stream>>>(h.d, s->nb, dcnt, s->img_off, s->img, n, -1);
+	CK(cudaGetLastError());
+	CK(cudaStreamSynchronize(s->stream));     /* the host vectors go out of scope */
+	h.n += n;
 	return 0;
 }
 

@@ -131,12 +131,17 @@ class Sim:
         self.ny_local = self.params.ny // self.params.nranks
 
     @classmethod
-    def from_conf(cls, path, rank=0, nranks=1, device=-1, ref_nprocs=1):
-        """sim_init (src/sim.c:238-320)."""
+    def from_conf(cls, path, rank=0, nranks=1, device=-1, ref_nprocs=1, stream_batch=0):
+        """sim_init (src/sim.c:238-320). stream_batch > 0: the population is generated and uploaded in
+        batches of that many particles (host memory stays small whatever the population)."""
         L = lib()
         h = C.c_void_p()
         r = RunC()
-        check(L.cpic_b200_sim_from_conf(str(path).encode(), rank, nranks, device, ref_nprocs, C.byref(h), C.byref(r)))
+        if stream_batch > 0:
+            check(L.cpic_b200_sim_from_conf_streamed(str(path).encode(), rank, nranks, device, ref_nprocs,
+                                                     stream_batch, C.byref(h), C.byref(r)))
+        else:
+            check(L.cpic_b200_sim_from_conf(str(path).encode(), rank, nranks, device, ref_nprocs, C.byref(h), C.byref(r)))
         params, run = load_conf(path, rank, nranks, device)
         return cls(params, _handle=h, _run=run)
 

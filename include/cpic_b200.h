@@ -84,6 +84,19 @@ int cpic_b200_comm_init(cpic_b200_sim_t *sim, const void *id128);
 int cpic_b200_set_particles(cpic_b200_sim_t *sim, int species, int64_t n,
 		const int64_t *id, const double *x, const double *y,
 		const double *ux, const double *uy, const double *uz);
+/* Streamed plasma_init for populations whose host arrays do not fit at once (1e9 particles; the
+ * reference's own host lists need 112 B per particle, src/def.h:88-133). The caller generates the
+ * population twice, batch by batch: cpic_b200_count_particles tallies every batch per particle
+ * block on the host (particles of every rank's slab are accepted and tallied, so that ranks which
+ * all see the whole stream arrive at one common capacity); cpic_b200_reserve_counted sizes the
+ * species from the tallies; then cpic_b200_add_particles bins every batch of this rank's slab
+ * (stable) and appends it to the blocks. A block ends up
+ * holding its particles in batch order, then input order (cpic_b200_set_particles: input order). */
+int cpic_b200_count_particles(cpic_b200_sim_t *sim, int species, int64_t n, const double *x, const double *y);
+int cpic_b200_reserve_counted(cpic_b200_sim_t *sim, int species);
+int cpic_b200_add_particles(cpic_b200_sim_t *sim, int species, int64_t n, const int64_t *id,
+		const double *x, const double *y, const double *ux, const double *uy, const double *uz);
+
 /* Block capacity (slots per particle block) of a species. With several ranks every rank must
  * use the same capacity (the exchange buffers are sized from it): set_particles on every
  * rank, take the maximum of cpic_b200_capacity over the ranks, and if it differs from the
@@ -195,6 +208,18 @@ int cpic_b200_conf_params(const cpic_b200_conf_t *conf, int rank, int nranks, in
 int cpic_b200_conf_init_particles(const cpic_b200_conf_t *conf, int ref_nprocs,
 		int64_t *const *id, double *const *x, double *const *y,
 		double *const *ux, double *const *uy);
+/* The stream of cpic_b200_conf_init_particles delivered in batches of at most `batch` particles of
+ * one species, in the order the reference draws them (process -> chunk -> species -> particle);
+ * `sink` returns non-zero to stop. */
+typedef int (*cpic_b200_particle_sink_t)(void *ctx, int species, int64_t n, const int64_t *id,
+		const double *x, const double *y, const double *ux, const double *uy);
+int cpic_b200_conf_stream_particles(const cpic_b200_conf_t *conf, int ref_nprocs, int64_t batch,
+		cpic_b200_particle_sink_t sink, void *ctx);
+/* cpic_b200_sim_from_conf with the streamed initialisation above: host memory stays at a few
+ * batches whatever the population (the particles are the same ones; inside a particle block they
+ * are ordered by batch instead of by id). */
+int cpic_b200_sim_from_conf_streamed(const char *path, int rank, int nranks, int device, int ref_nprocs,
+		int64_t batch, cpic_b200_sim_t **sim, cpic_b200_run_t *run);
 /* sim_init (reference src/sim.c:238-320): params, create, host init of all species,
  * upload of this rank's slab, and (single rank only) the pre-step. With several ranks
  * call cpic_b200_comm_init and cpic_b200_pre_step afterwards. */

@@ -35,8 +35,13 @@ def main():
         params.capacity_factor = 1.01        # forces the collective capacity growth (check_capacity)
     parts = init_particles(conf)
     o = oracle_from(params, parts)
-    g = Sim(params)
-    set_particles_collective(g, partition(parts, params, rank), dist, device=dev)
+    if os.environ.get("MGPU_STREAMED"):
+        # sim_init with the streamed initialisation: every rank draws the whole population in batches,
+        # tallies all slabs (one capacity everywhere, no communication) and keeps its own
+        g = Sim.from_conf(conf, rank=rank, nranks=world, device=local, stream_batch=int(os.environ["MGPU_STREAMED"]))
+    else:
+        g = Sim(params)
+        set_particles_collective(g, partition(parts, params, rank), dist, device=dev)
     bootstrap(g, dist, device=dev)
     o.pre_step()
     g.pre_step()

@@ -234,3 +234,40 @@ def test_image_round_trip_is_exact():
         pa, pb = a.particles(i), b.particles(i)
         for k in ("id", "x", "y", "ux", "uy"):
             assert np.array_equal(pa[k], pb[k]), (i, k)
+
+
+@pytest.mark.parametrize("conf,batch", [("2d-2species-small.conf", 777), ("two-streams.conf", 64), ("far-beam.conf", 1 << 20)])
+def test_streamed_initialisation(conf, batch):
+    """cpic_b200_sim_from_conf_streamed: the reference's initial conditions generated and uploaded in
+    batches (count, reserve, append). Same particles, same capacity as the one-shot path; inside a block
+    they are ordered by batch, so sums differ in the last bits only."""
+    g, o, params, _ = pair_from_conf(conf_path(conf))
+    s = Sim.from_conf(conf_path(conf), stream_batch=batch)
+    for i in range(len(params.q)):
+        assert s.capacity(i) == g.capacity(i)
+        assert s.num_particles(i) == g.num_particles(i)
+    for it in range(5):
+        s.sync()
+        assert_close(field_errors(s, o), what=f"{conf} streamed, iteration {it}")
+        assert_close(particle_errors(s, o, params), what=f"{conf} streamed, iteration {it}")
+        s.step()
+        o.step()
+
+
+def test_streamed_initialisation_rejects_misuse():
+    p = Params(64, 64, 4.0, 4.0, 0.01, 1.0)
+    s = Sim(p)
+    x = np.array([1.0, 5.0])
+    y = np.array([1.0, 1.0])
+    L = s.L
+    ptr = lambda a: a.ctypes.data
+    assert L.cpic_b200_reserve_counted(s.h, 0) != 0                      # nothing counted yet
+    assert L.cpic_b200_count_particles(s.h, 0, 2, ptr(x), ptr(y)) != 0   # x = 5 is outside [0, 4]
+    ids = np.arange(1, dtype=np.int64)
+    one = np.array([1.0])
+    assert L.cpic_b200_add_particles(s.h, 0, 1, ptr(ids), ptr(one), ptr(one), ptr(one), ptr(one), None) != 0  # no storage
+    assert L.cpic_b200_count_particles(s.h, 0, 1, ptr(one), ptr(one)) == 0
+    assert L.cpic_b200_reserve_counted(s.h, 0) == 0
+    assert L.cpic_b200_add_particles(s.h, 0, 1, ptr(ids), ptr(one), ptr(one), ptr(one), ptr(one), None) == 0
+    assert s.num_particles(0) == 1
+

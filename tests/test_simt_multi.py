@@ -57,3 +57,8 @@ def test_four_ranks_on_cpu(simt_build):
 def test_capacity_growth_is_agreed_between_ranks_on_cpu(simt_build):
     out = run_ranks_cpu(simt_build, 2, "uniform-small.conf", 40, env={"MGPU_TIGHT": "1"})
     assert "MGPU-CAPS" in out
+
+
+def test_streamed_initialisation_on_two_ranks_on_cpu(simt_build):
+    run_ranks_cpu(simt_build, 2, "2d-2species-small.conf", 6, env={"MGPU_STREAMED": "1000"})
+
