@@ -666,24 +666,43 @@ occupancy(sim_t_ *s, int is, int64_t out[6])
 	CK(cudaMemcpyAsync(cnt.data(), h.d.count, cnt.size() * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
 	CK(cudaMemcpyAsync(oc.data(), h.d.ob[h.arr].count, oc.size() * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
 	CK(cudaStreamSynchronize(s->stream));
-	/* a block's next segment can hold everything it has now plus what is on its way */
+	/* a block's next segment must hold everything it has now plus what is on its way from its
+	 * eight neighbours (the same neighbour walk as find_arrivals, kernels.cuh) */
+	const Geom &g = s->g;
 	int64_t mb = 0, ms = 0, mc = 0;
-	for(int b = 0; b < s->nb; b++) mb = std::max<int64_t>(mb, cnt[(size_t) b]);
-	int64_t pending = 0;
+	for(int b = 0; b < s->nb; b++)
+	{
+		const int bx = b % g.nbx, by = b / g.nbx;
+		int64_t need = cnt[(size_t) b];
+		for(int k = 0; k < 9; k++)
+		{
+			if(k == DEST_STAY) continue;
+			int nx_ = bx + k % 3 - 1, ny_ = by + k / 3 - 1, src;
+			if(nx_ < 0) nx_ += g.nbx; else if(nx_ >= g.nbx) nx_ -= g.nbx;
+			if(g.nby_glob == g.nby)
+			{
+				if(ny_ < 0) ny_ += g.nby; else if(ny_ >= g.nby) ny_ -= g.nby;
+				src = ny_ * g.nbx + nx_;
+			}
+			else if(ny_ < 0) src = s->nb + nx_;                /* north ghost row */
+			else if(ny_ >= g.nby) src = s->nb + g.nbx + nx_;   /* south ghost row */
+			else src = ny_ * g.nbx + nx_;
+			need += oc[(size_t) (8 - k) * s->nob + (size_t) src];
+		}
+		mb = std::max(mb, need);
+	}
 	for(int c = 0; c < 9; c++)
 	{
 		if(c == DEST_STAY) continue;
 		for(int b = 0; b < s->nob; b++)
 		{
 			const int v = oc[(size_t) c * s->nob + b];
-			pending = std::max<int64_t>(pending, v);
 			if(c & 1) ms = std::max<int64_t>(ms, v); else mc = std::max<int64_t>(mc, v);
 		}
 	}
-	out[0] = mb + 2 * ms + mc; out[1] = h.d.cap;
+	out[0] = mb; out[1] = h.d.cap;
 	out[2] = ms; out[3] = h.d.ocs;
 	out[4] = mc; out[5] = h.d.occ;
-	(void) pending;
 	return 0;
 }
 
@@ -788,6 +807,19 @@ absorb(sim_t_ *s, int is)
 {
 	SpeciesHost &h = s->sp[is];
 	if(!h.block) return 0;
+	/* arrivals that would not fit: a larger segment takes them (regrow merges them on the way);
+	 * with several ranks the capacity is a collective decision, so it is an error here */
+	int64_t o[6];
+	int rc = occupancy(s, is, o);
+	if(rc) return rc;
+	if(o[0] > o[1])
+	{
+		if(s->comm)
+			return fail(CPIC_B200_ECAPACITY, "species %d: a block holds %lld particles with its arrivals, capacity %lld: "
+					"raise capacity_factor (now %g) or call cpic_b200_sync more often", is, (long long) o[0], (long long) o[1],
+					s->p.capacity_factor);
+		return regrow(s, is, (int) std::min<int64_t>(((o[0] * 3 / 2 + 31) / 32) * 32, 1 << 30));
+	}
 	k_absorb<<<(s->nb + 7) / 8, 256, 0, s->stream>>>(h.d, s->g, s->nb, h.arr, s->errflag);
 	cudaError_t e = cudaGetLastError();
 	if(e != cudaSuccess) return fail(CPIC_B200_ECUDA, "kernel launch failed: %s", cudaGetErrorString(e));
