@@ -30,10 +30,21 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     else:
         dist.init_process_group("gloo")
-    params, run = load_conf(conf, rank=rank, nranks=world, device=local)
+    if conf.startswith("random:"):
+        # a random configuration of tests/test_gpu_parity.py::_random_case, the same on every rank
+        from test_gpu_parity import _random_case
+        params, parts, _, _ = _random_case(int(conf.split(":")[1]))
+        params.rank, params.nranks, params.device = rank, world, local
+        if params.ny % world or (params.ny // world) % max(params.block_cells, 1):
+            if rank == 0:
+                print(f"MGPU-OK world={world} conf={conf} skipped (slab height)")
+            dist.destroy_process_group()
+            return
+    else:
+        params, run = load_conf(conf, rank=rank, nranks=world, device=local)
+        parts = init_particles(conf)
     if os.environ.get("MGPU_TIGHT"):
         params.capacity_factor = 1.01        # forces the collective capacity growth (check_capacity)
-    parts = init_particles(conf)
     o = oracle_from(params, parts)
     if os.environ.get("MGPU_STREAMED"):
         # sim_init with the streamed initialisation: every rank draws the whole population in batches,
