@@ -752,7 +752,9 @@ k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 			if(leave)
 			{
 				if((peers & lt) == 0) ocnt[dest] = pos + __popc(peers);
-				if(dest == DEST_FAR)
+				/* a leaver whose region is full takes the far movers' road: listed now, placed in its
+				 * new block by k_far_insert (in id order, so the result stays deterministic) */
+				if(dest == DEST_FAR || pos >= sp.rcap[dest])
 				{
 					const int k = atomicAdd(sp.fcount, 1);
 					if(k < FAR_CAP)
@@ -764,7 +766,7 @@ k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 					}
 					else bad |= 16;
 				}
-				else if(pos < sp.rcap[dest])
+				else
 				{
 					const size_t o = region_slot(sp, dest, b, pos);
 					double2 *r = (double2 *) (out.rec + o * OREC);
@@ -773,7 +775,6 @@ k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 					r[2] = make_double2(uz, __longlong_as_double(pid));
 					if(out.recE) *(double2 *) (out.recE + o * 2) = make_double2(Ex, Ey);
 				}
-				else bad |= 8;
 			}
 			__syncwarp();
 		}

@@ -336,3 +336,26 @@ def test_random_configurations(first):
             g.close()
     assert ran >= 10
 
+
+def test_full_exchange_regions_spill_into_the_far_list():
+    """A beam that sends ~200 particles per block and step across one face into regions of 64 slots:
+    the leavers that do not fit are listed like far movers and placed by k_far_insert -- same
+    particles, same fields as the oracle, no refusal."""
+    rng = np.random.default_rng(5)
+    nx = ny = 64
+    dx, dt = 0.5, 0.05
+    p = Params(nx, ny, nx * dx, ny * dx, dt, 1e4, (0.0, 0.0, 0.0), (-1.0,), (1.0,), 1, block_cells=8, outbox_fraction=0.05)
+    n = 30000
+    parts = [{"id": np.arange(n, dtype=np.int64), "x": rng.random(n) * p.Lx, "y": rng.random(n) * p.Ly,
+              "ux": np.full(n, 5 * dx / dt), "uy": np.full(n, -3 * dx / dt), "uz": np.zeros(n)}]
+    o = oracle_from(p, parts)
+    g = gpu_from(p, parts)
+    o.pre_step()
+    g.pre_step()
+    assert g.occupancy(0)["side_cap"] == 64
+    for it in range(3):
+        g.step()
+        o.step()
+        g.sync()
+        assert_close({**field_errors(g, o), **particle_errors(g, o, p)}, what=f"iteration {it}")
+
