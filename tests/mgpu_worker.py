@@ -32,7 +32,7 @@ def main():
         dist.init_process_group("gloo")
     if conf.startswith("random:"):
         # a random configuration of tests/test_gpu_parity.py::_random_case, the same on every rank
-        from test_gpu_parity import _random_case
+        from test_gpu_zz_robustness import _random_case
         params, parts, _, _ = _random_case(int(conf.split(":")[1]))
         params.rank, params.nranks, params.device = rank, world, local
         if params.ny % world or (params.ny // world) % max(params.block_cells, 1):
@@ -63,12 +63,20 @@ def main():
     def check(tag):
         g.sync()
         e = {}
-        e["rho"] = relerr(g.field("rho"), o.field("rho")[r0:r0 + nyl])
+
+        def slab_err(mine, ref_slab, ref_all):
+            # max|a - b| over this rank's rows against max|b| over the WHOLE field: a slab
+            # whose own values happen to be small must not inflate the measure
+            scale = np.abs(ref_all).max() if ref_all.size else 0.0
+            d = np.abs(np.asarray(mine) - np.asarray(ref_slab)).max() if ref_slab.size else 0.0
+            return d / scale if scale > 0 else d
+
+        e["rho"] = slab_err(g.field("rho"), o.field("rho")[r0:r0 + nyl], o.field("rho"))
         og = o.field("phi_ghost")          # rows: -1, 0 .. ny-1, ny, ny+1 (periodic images)
         rows = [(r0 - 1 + k) % params.ny for k in range(nyl + 3)]
-        e["phi"] = relerr(g.field("phi_ghost"), og[1:params.ny + 1][rows])
-        e["Ex"] = relerr(g.field("Ex"), o.field("Ex")[r0:r0 + nyl + 1])
-        e["Ey"] = relerr(g.field("Ey"), o.field("Ey")[r0:r0 + nyl + 1])
+        e["phi"] = slab_err(g.field("phi_ghost"), og[1:params.ny + 1][rows], og)
+        e["Ex"] = slab_err(g.field("Ex"), o.field("Ex")[r0:r0 + nyl + 1], o.field("Ex"))
+        e["Ey"] = slab_err(g.field("Ey"), o.field("Ey")[r0:r0 + nyl + 1], o.field("Ey"))
         from cpic_b200.dist import slab_rank
         for i in range(len(params.q)):
             a, b = g.particles(i), o.particles(i)

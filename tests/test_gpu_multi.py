@@ -48,10 +48,3 @@ def test_two_ranks_capacity_growth():
         pytest.skip("needs 2 GPUs")
     out = run_ranks(2, "uniform-small.conf", 40, "fused", port=29615, env={"MGPU_TIGHT": "1"})
     assert "MGPU-CAPS" in out
-
-
-def test_two_ranks_streamed_initialisation():
-    if ngpus() < 2:
-        pytest.skip("needs 2 GPUs")
-    run_ranks(2, "2d-2species-small.conf", 6, port=29617, env={"MGPU_STREAMED": "1000"})
-
