@@ -196,14 +196,8 @@ tma_bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
 			:: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-/* 8-byte asynchronous global->shared copy (LDGSTS): the particle pipeline's prefetch */
-__device__ __forceinline__ void
-cp_async8(void *dst, const void *src)
-{
-	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(smem_u32(dst)), "l"(src) : "memory");
-}
-
-/* 16-byte variant, L2 only (the segment batches are streamed once) */
+/* 16-byte asynchronous global->shared copy (LDGSTS.128), L2 only: the particle pipeline's
+ * prefetch of arrival records (and of segment batches with OWN_BULK=0); streamed once */
 __device__ __forceinline__ void
 cp_async16(void *dst, const void *src)
 {
