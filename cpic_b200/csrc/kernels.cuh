@@ -50,13 +50,21 @@
 #define SEG_STEP ((size_t) sp.astride)
 #endif
 
-__host__ __device__ __forceinline__ size_t
+/* Slot numbers of the plain layout fit 32 bits (checked when a species is allocated): one
+ * IMAD.WIDE per access instead of 64-bit address chains */
+#if SEG_AOSOA
+typedef size_t seg_index_t;
+#else
+typedef unsigned seg_index_t;
+#endif
+
+__host__ __device__ __forceinline__ seg_index_t
 seg_slot(int cap, int b, int i)
 {
 #if SEG_AOSOA
 	return ((size_t) b * cap + (size_t) (i & ~31)) * 6 + (size_t) (i & 31);
 #else
-	return (size_t) b * cap + (size_t) i;
+	return (unsigned) b * (unsigned) cap + (unsigned) i;
 #endif
 }
 
@@ -556,7 +564,7 @@ k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 			uint64_t *mb_ = sbar + (bi) % PIPE_STAGES; \
 			const int na_ = (MODE == 0 ? 2 : 5) + ((MODE != 0 && (with_id)) ? 1 : 0) + (MODE == 1 ? 2 : 0); \
 			mbar_expect_tx(mb_, (uint32_t) na_ * 256u); \
-			const size_t g_ = seg_slot(sp.cap, b, (bi) * 32); \
+			const seg_index_t g_ = seg_slot(sp.cap, b, (bi) * 32); \
 			if(SEG_AOSOA) { \
 				/* the batch's arrays are contiguous: one copy */ \
 				tma_bulk_load(st0_, sp.x + g_, (MODE == 0 ? 2u : (with_id) ? 6u : 5u) * 256u, mb_); \
@@ -719,7 +727,7 @@ k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 			if(dpos < sp.cap)
 			{
 				const unsigned d = base + dpos;
-				const size_t ds = seg_slot(sp.cap, b, dpos);
+				const seg_index_t ds = seg_slot(sp.cap, b, dpos);
 				if(pp.set_r || moved) { sp.x[ds] = x; sp.y[ds] = y; }
 				sp.ux[ds] = ux; sp.uy[ds] = uy; sp.uz[ds] = uz;
 				if(moved) sp.id[ds] = pid;
