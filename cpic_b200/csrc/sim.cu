@@ -807,22 +807,29 @@ absorb(sim_t_ *s, int is)
 {
 	SpeciesHost &h = s->sp[is];
 	if(!h.block) return 0;
-	/* arrivals that would not fit: a larger segment takes them (regrow merges them on the way);
-	 * with several ranks the capacity is a collective decision, so it is an error here */
-	int64_t o[6];
-	int rc = occupancy(s, is, o);
-	if(rc) return rc;
-	if(o[0] > o[1])
+	/* k_absorb leaves a block alone when its arrivals would not fit and says so in its own flag word
+	 * (errflag[15]); a larger segment then takes them (regrow merges them on the way). With several
+	 * ranks the capacity is a collective decision, so it is an error here. */
+	int *flag = s->errflag + 15;
+	CK(cudaMemsetAsync(flag, 0, sizeof(int), s->stream));
+	k_absorb<<<(s->nb + 7) / 8, 256, 0, s->stream>>>(h.d, s->g, s->nb, h.arr, flag);
 	{
+		cudaError_t e = cudaGetLastError();
+		if(e != cudaSuccess) return fail(CPIC_B200_ECUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+	}
+	CK(cudaMemcpyAsync(s->h_err + 15, flag, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+	CK(cudaStreamSynchronize(s->stream));
+	if(s->h_err[15])
+	{
+		int64_t o[6];
+		int rc = occupancy(s, is, o);
+		if(rc) return rc;
 		if(s->comm)
 			return fail(CPIC_B200_ECAPACITY, "species %d: a block holds %lld particles with its arrivals, capacity %lld: "
 					"raise capacity_factor (now %g) or call cpic_b200_sync more often", is, (long long) o[0], (long long) o[1],
 					s->p.capacity_factor);
-		return regrow(s, is, (int) std::min<int64_t>(((o[0] * 3 / 2 + 31) / 32) * 32, 1 << 30));
+		return regrow(s, is, (int) std::min<int64_t>(((std::max(o[0], o[1] + 1) * 3 / 2 + 31) / 32) * 32, 1 << 30));
 	}
-	k_absorb<<<(s->nb + 7) / 8, 256, 0, s->stream>>>(h.d, s->g, s->nb, h.arr, s->errflag);
-	cudaError_t e = cudaGetLastError();
-	if(e != cudaSuccess) return fail(CPIC_B200_ECUDA, "kernel launch failed: %s", cudaGetErrorString(e));
 	return 0;
 }
 

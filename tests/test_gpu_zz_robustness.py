@@ -136,6 +136,43 @@ def test_full_exchange_regions_spill_into_the_far_list():
         assert_close({**field_errors(g, o), **particle_errors(g, o, p)}, what=f"iteration {it}")
 
 
+def test_host_getters_grow_a_segment_that_cannot_take_its_arrivals():
+    """A uniform species collapsing onto a cluster of opposite charge: a block ends up with arrivals
+    from all eight neighbours. Without a cpic_b200_sync in between nothing has grown the capacity;
+    reading the particles must do it rather than drop the arrivals."""
+    rng = np.random.default_rng(1743)
+    nx, ny, dx, dt, n = 64, 32, 0.5, 0.05, 3000
+    p = Params(nx, ny, nx * dx, ny * dx, dt, 1.0, (0.0, 0.0, 0.5), (1.0, -2.0), (0.5, 1.0), 1, block_cells=4)
+    v = dx / dt
+    parts = [{"id": np.arange(n, dtype=np.int64), "x": rng.random(n) * p.Lx, "y": rng.random(n) * p.Ly,
+              "ux": (rng.random(n) * 2 - 1) * v, "uy": (rng.random(n) * 2 - 1) * v, "uz": np.zeros(n)},
+             {"id": np.arange(n, 2 * n, dtype=np.int64), "x": (rng.normal(0.5, 0.05, n) % 1.0) * p.Lx,
+              "y": (rng.normal(0.5, 0.05, n) % 1.0) * p.Ly,
+              "ux": (rng.random(n) * 2 - 1) * v, "uy": (rng.random(n) * 2 - 1) * v, "uz": np.zeros(n)}]
+    o = oracle_from(p, parts)
+    g = gpu_from(p, parts)
+    o.pre_step()
+    g.pre_step()
+    cap0 = g.capacity(0)
+    for it in range(8):
+        g.step()
+        o.step()
+        occ = g.occupancy(0)               # read-only: own particles + pending arrivals of the fullest block
+        if occ["block"] > occ["block_cap"]:
+            break
+    else:
+        pytest.fail("the population never outgrew a segment: the case no longer exercises the path")
+    assert sum(len(g.particles(i)["id"]) for i in range(len(p.q))) == sum(len(q["id"]) for q in parts)
+    assert g.capacity(0) > cap0
+    g.sync()
+    assert_close(particle_errors(g, o, p), tol=1e-9, what="after the growth")
+    for it in range(3):
+        g.step()
+        o.step()
+    g.sync()
+    assert_close(particle_errors(g, o, p), tol=1e-8, what="three steps later")
+
+
 def test_two_ranks_streamed_initialisation():
     from test_gpu_multi import ngpus, run_ranks
     if ngpus() < 2:
