@@ -142,35 +142,10 @@ struct PushParams {
 
 /* ------------------------------------------------------------------------ TMA */
 
-/* The primitives below take shared-memory addresses in the 32-bit shared window. SA(p) makes one
- * from a pointer: by a generic->shared conversion at every use (SMEM_ADDR32 0: what the compiler
- * emits is S2UR + UMOV + ULEA each time, about thirty instructions per batch of the push), or
- * from the window address of the dynamic shared array taken once per thread plus a pointer
- * difference (SMEM_ADDR32 1; needs `smem` and `smem32` in scope). */
-#ifndef SMEM_ADDR32
-#define SMEM_ADDR32 0
-#endif
-
 #ifdef CPIC_B200_SIMT_CHECK
-/* tests/simt (CPU test suite): the same six primitives run by a lockstep SIMT interpreter,
- * which works on the pointers themselves */
+/* tests/simt (CPU test suite): the same six primitives run by a lockstep SIMT interpreter */
 #include "simt_async.h"
-#if SMEM_ADDR32
-/* the pointer arithmetic of the 32-bit form is still exercised */
-#define SA(p) ((void *) ((unsigned char *) smem + (uint32_t) ((const char *) (p) - (const char *) smem)))
 #else
-#define SA(p) ((void *) (p))
-#endif
-#define SMEM32_DECL
-#else
-
-#if SMEM_ADDR32
-#define SA(p) (smem32 + (uint32_t) ((const char *) (p) - (const char *) smem))
-#define SMEM32_DECL const uint32_t smem32 = smem_u32(smem);
-#else
-#define SA(p) smem_u32(p)
-#define SMEM32_DECL
-#endif
 
 __device__ __forceinline__ uint32_t
 smem_u32(const void *p)
@@ -179,23 +154,23 @@ smem_u32(const void *p)
 }
 
 __device__ __forceinline__ void
-mbar_init(uint32_t bar, int count)
+mbar_init(uint64_t *bar, int count)
 {
-	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count));
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
 	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
 
 __device__ __forceinline__ void
-mbar_expect_tx(uint32_t bar, uint32_t bytes)
+mbar_expect_tx(uint64_t *bar, uint32_t bytes)
 {
 	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
-			:: "r"(bar), "r"(bytes) : "memory");
+			:: "r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 
 /* Returns 0 on success, 1 when the barrier did not complete (descriptor error): the
  * caller raises an error flag instead of hanging the device. */
 __device__ __forceinline__ int
-mbar_wait(uint32_t bar, uint32_t parity)
+mbar_wait(uint64_t *bar, uint32_t parity)
 {
 	uint32_t done = 0;
 	for(int spin = 0; spin < (1 << 22); spin++)
@@ -203,7 +178,7 @@ mbar_wait(uint32_t bar, uint32_t parity)
 		asm volatile("{\n\t.reg .pred p;\n\t"
 				"mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
 				"selp.u32 %0, 1, 0, p;\n\t}"
-				: "=r"(done) : "r"(bar), "r"(parity) : "memory");
+				: "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
 		if(done) return 0;
 	}
 	return 1;
@@ -212,29 +187,29 @@ mbar_wait(uint32_t bar, uint32_t parity)
 /* 2D tile load: box (TW x TH doubles) of a row-major array whose first coordinate is
  * the column. Out-of-range elements are zero-filled by the TMA unit. */
 __device__ __forceinline__ void
-tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar)
+tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar)
 {
 	asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
 			" [%0], [%1, {%2, %3}], [%4];"
-			:: "r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
+			:: "r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
 			: "memory");
 }
 
 /* 1D bulk copy global->shared through the TMA unit (UBLKCP): `bytes` multiple of 16, both
  * addresses 16 B aligned; completes on the mbarrier */
 __device__ __forceinline__ void
-tma_bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+tma_bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
 {
 	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-			:: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+			:: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
 /* 16-byte asynchronous global->shared copy (LDGSTS.128), L2 only: the particle pipeline's
  * prefetch of arrival records (and of segment batches with OWN_BULK=0); streamed once */
 __device__ __forceinline__ void
-cp_async16(uint32_t dst, const void *src)
+cp_async16(void *dst, const void *src)
 {
-	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_u32(dst)), "l"(src) : "memory");
 }
 
 __device__ __forceinline__ void
@@ -516,7 +491,6 @@ k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 {
 	constexpr int NARR = PipeArrays<MODE>::N;
 	extern __shared__ __align__(128) unsigned char smem[];
-	SMEM32_DECL
 	uint64_t *bar = (uint64_t *) smem;                                  /* E tile barrier */
 	uint64_t *sbar = (uint64_t *) (smem + 16) + (threadIdx.x >> 5) * PIPE_STAGES;   /* per warp, per stage */
 	int *wscratch = (int *) (smem + PUSH_SMEM_HEADER) + (threadIdx.x >> 5) * 32;   /* 32 ints per warp */
@@ -533,16 +507,16 @@ k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 	const int b = by * g.nbx + bx;
 	int *ocnt = wscratch + 18;       /* leavers per destination code so far */
 	if(lane < 9) ocnt[lane] = 0;
-	if(lane < PIPE_STAGES) mbar_init(SA(sbar + lane), 1);
+	if(lane < PIPE_STAGES) mbar_init(sbar + lane, 1);
 	__syncwarp();
 
 	if(MODE != 1 && threadIdx.x == 0)
 	{
-		mbar_init(SA(bar), 1);
+		mbar_init(bar, 1);
 		uint32_t bytes = 2u * (uint32_t) (g.TH * g.TW) * 8u;
-		mbar_expect_tx(SA(bar), bytes);
-		tma_load_2d(SA(tEx), &mapEx, cx * g.WPC * g.BX, by * g.BY, SA(bar));
-		tma_load_2d(SA(tEy), &mapEy, cx * g.WPC * g.BX, by * g.BY, SA(bar));
+		mbar_expect_tx(bar, bytes);
+		tma_load_2d(tEx, &mapEx, cx * g.WPC * g.BX, by * g.BY, bar);
+		tma_load_2d(tEy, &mapEy, cx * g.WPC * g.BX, by * g.BY, bar);
 	}
 
 	/* MODE 0 leaves the arrivals where they are (outbox `cur`); a push consumes the
@@ -575,31 +549,31 @@ k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 		const unsigned h_ = lane >> 4; \
 		/* array a of the batch starts a*SEG_STEP doubles after its x values */ \
 		const double *g_ = sp.x + seg_slot(sp.cap, b, (bi) * 32) + (lane & 15) * 2 + (size_t) h_ * SEG_STEP; \
-		cp_async16(SA(d_), g_); \
+		cp_async16(d_, g_); \
 		if(MODE != 0) { \
-			cp_async16(SA(d_ + 64), g_ + 2 * SEG_STEP); \
-			if(h_ == 0 || (with_id)) cp_async16(SA(d_ + 128), g_ + 4 * SEG_STEP); \
+			cp_async16(d_ + 64, g_ + 2 * SEG_STEP); \
+			if(h_ == 0 || (with_id)) cp_async16(d_ + 128, g_ + 4 * SEG_STEP); \
 		} \
-		if(MODE == 1) cp_async16(SA(d_ + 192), (h_ ? sp.pEy : sp.pEx) + q_); \
+		if(MODE == 1) cp_async16(d_ + 192, (h_ ? sp.pEy : sp.pEx) + q_); \
 		cp_async_commit(); \
 	} else if(own_) { \
 		/* a whole batch of the segment is 256 contiguous, aligned bytes per array: one TMA \
 		 * bulk copy each, issued by one lane, landing on the stage's mbarrier */ \
 		if(lane == 0) { \
 			const unsigned q_ = base + (bi) * 32; \
-			const auto mb_ = SA(sbar + (bi) % PIPE_STAGES); \
+			uint64_t *mb_ = sbar + (bi) % PIPE_STAGES; \
 			const int na_ = (MODE == 0 ? 2 : 5) + ((MODE != 0 && (with_id)) ? 1 : 0) + (MODE == 1 ? 2 : 0); \
 			mbar_expect_tx(mb_, (uint32_t) na_ * 256u); \
 			const seg_index_t g_ = seg_slot(sp.cap, b, (bi) * 32); \
 			if(SEG_AOSOA) { \
 				/* the batch's arrays are contiguous: one copy */ \
-				tma_bulk_load(SA(st0_), sp.x + g_, (MODE == 0 ? 2u : (with_id) ? 6u : 5u) * 256u, mb_); \
+				tma_bulk_load(st0_, sp.x + g_, (MODE == 0 ? 2u : (with_id) ? 6u : 5u) * 256u, mb_); \
 			} else { \
-			tma_bulk_load(SA(st0_ + 0 * 32), sp.x + g_, 256, mb_); tma_bulk_load(SA(st0_ + 1 * 32), sp.y + g_, 256, mb_); \
-			if(MODE != 0) { tma_bulk_load(SA(st0_ + 2 * 32), sp.ux + g_, 256, mb_); tma_bulk_load(SA(st0_ + 3 * 32), sp.uy + g_, 256, mb_); \
-				tma_bulk_load(SA(st0_ + 4 * 32), sp.uz + g_, 256, mb_); if(with_id) tma_bulk_load(SA(st0_ + 5 * 32), sp.id + g_, 256, mb_); } \
+			tma_bulk_load(st0_ + 0 * 32, sp.x + g_, 256, mb_); tma_bulk_load(st0_ + 1 * 32, sp.y + g_, 256, mb_); \
+			if(MODE != 0) { tma_bulk_load(st0_ + 2 * 32, sp.ux + g_, 256, mb_); tma_bulk_load(st0_ + 3 * 32, sp.uy + g_, 256, mb_); \
+				tma_bulk_load(st0_ + 4 * 32, sp.uz + g_, 256, mb_); if(with_id) tma_bulk_load(st0_ + 5 * 32, sp.id + g_, 256, mb_); } \
 			} \
-			if(MODE == 1) { tma_bulk_load(SA(st0_ + 6 * 32), sp.pEx + q_, 256, mb_); tma_bulk_load(SA(st0_ + 7 * 32), sp.pEy + q_, 256, mb_); } \
+			if(MODE == 1) { tma_bulk_load(st0_ + 6 * 32, sp.pEx + q_, 256, mb_); tma_bulk_load(st0_ + 7 * 32, sp.pEy + q_, 256, mb_); } \
 		} \
 	} else { \
 		/* arrivals are scattered over up to eight runs of records: per lane three 16-byte async \
@@ -609,9 +583,9 @@ k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 		if(t_ < A.total) { \
 			const size_t q_ = arrival_slot(A, sp, t_); \
 			const double *r_ = in.rec + q_ * OREC; \
-			cp_async16(SA(st_), r_); \
-			if(MODE != 0) { cp_async16(SA(st_ + 64), r_ + 2); cp_async16(SA(st_ + 128), r_ + 4); } \
-			if(MODE == 1) cp_async16(SA(st_ + 192), in.recE + q_ * 2); \
+			cp_async16(st_, r_); \
+			if(MODE != 0) { cp_async16(st_ + 64, r_ + 2); cp_async16(st_ + 128, r_ + 4); } \
+			if(MODE == 1) cp_async16(st_ + 192, in.recE + q_ * 2); \
 		} \
 		cp_async_commit(); \
 	} } while(0)
@@ -640,7 +614,7 @@ k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 	if(MODE != 1)
 	{
 		__syncthreads();
-		if(mbar_wait(SA(bar), 0))
+		if(mbar_wait(bar, 0))
 		{
 			if(threadIdx.x == 0) atomicOr(errflag, ERRBIT_TMA);
 			cp_async_wait<0>();
@@ -670,7 +644,7 @@ k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 		 * PIPE_STAGES-1 (every batch index >= nbo, real or not, commits exactly one group) */
 		if(own && OWN_BULK)
 		{
-			if(mbar_wait(SA(sbar + bi % PIPE_STAGES), (bi / PIPE_STAGES) & 1)) { atomicOr(errflag, ERRBIT_TMA); break; }
+			if(mbar_wait(sbar + bi % PIPE_STAGES, (bi / PIPE_STAGES) & 1)) { atomicOr(errflag, ERRBIT_TMA); break; }
 		}
 		else
 		{

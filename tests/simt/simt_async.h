@@ -5,22 +5,22 @@
 #ifndef SIMT_ASYNC_H
 #define SIMT_ASYNC_H
 
-static inline void mbar_init(void *bar, int count) { simt::bar_init((uint64_t *) bar, count); }
-static inline void mbar_expect_tx(void *bar, uint32_t bytes) { simt::bar_expect_tx((uint64_t *) bar, bytes); }
+static inline void mbar_init(uint64_t *bar, int count) { simt::bar_init(bar, count); }
+static inline void mbar_expect_tx(uint64_t *bar, uint32_t bytes) { simt::bar_expect_tx(bar, bytes); }
 
 static inline int
-mbar_wait(void *bar, uint32_t parity)
+mbar_wait(uint64_t *bar, uint32_t parity)
 {
 	for(int spin = 0; spin < 4096; spin++)
 	{
-		if(simt::bar_try_wait((uint64_t *) bar, parity)) return 0;
+		if(simt::bar_try_wait(bar, parity)) return 0;
 		simt::yield();
 	}
 	return 1;
 }
 
-static inline void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, void *bar) { simt::bar_tensor_load_2d(dst, map, c0, c1, (uint64_t *) bar); }
-static inline void tma_bulk_load(void *dst, const void *src, uint32_t bytes, void *bar) { simt::bar_bulk_load(dst, src, bytes, (uint64_t *) bar); }
+static inline void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) { simt::bar_tensor_load_2d(dst, map, c0, c1, bar); }
+static inline void tma_bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) { simt::bar_bulk_load(dst, src, bytes, bar); }
 static inline void cp_async8(void *dst, const void *src) { simt::async_copy8(dst, src); }
 static inline void cp_async16(void *dst, const void *src)
 {
