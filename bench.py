@@ -228,6 +228,9 @@ def main():
     import torch
     import torch.distributed as dist
     from cpic_b200 import Sim, Params, load_conf, init_particles
+    from cpic_b200._lib import lib as _cpic_lib
+    if "sm_100a" not in _cpic_lib().cpic_b200_version().decode():
+        raise SystemExit("bench.py measures the CUDA library only")
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

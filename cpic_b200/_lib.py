@@ -116,6 +116,11 @@ def lib():
             f = getattr(L, name)
             f.restype = res
             f.argtypes = args
+        version = L.cpic_b200_version().decode()
+        if "sm_100a" not in version and os.environ.get("CPIC_B200_SIMT_CHECK") != "1":
+            # CPIC_B200_LIB may name another build of the CUDA library, never a CPU one: the build
+            # that the test suite interprets on the CPU is only accepted inside that suite
+            raise ImportError(f"{path} is not a CUDA build of cpic_b200 ({version}); cpic_b200 has no CPU path")
         _lib = L
     return _lib
 

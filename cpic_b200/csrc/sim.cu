@@ -43,7 +43,13 @@ fail(int code, const char *fmt, ...)
 
 extern "C" const char *cpic_b200_last_error(void) { return g_err; }
 extern "C" void cpic_b200_set_error_(const char *msg) { snprintf(g_err, sizeof(g_err), "%s", msg); }
+#ifdef CPIC_B200_SIMT_CHECK
+/* tests/simt: this translation unit compiled for the CPU test interpreter says so, and the Python
+ * view refuses it outside the test suite */
+extern "C" const char *cpic_b200_version(void) { return "cpic_b200 0.1 (simt-check interpreter build: tests only)"; }
+#else
 extern "C" const char *cpic_b200_version(void) { return "cpic_b200 0.1 (sm_100a)"; }
+#endif
 
 /* ----------------------------------------------------------------- context */
 

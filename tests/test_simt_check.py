@@ -77,6 +77,14 @@ def test_product_library_is_not_the_interpreter():
             assert "simt" not in open(os.path.join(ROOT, "cpic_b200", name)).read(), name
 
 
+def test_the_python_view_refuses_the_interpreter_build_outside_the_test_suite(simt_build):
+    env = dict(os.environ, CPIC_B200_LIB=simt_build)
+    env.pop("CPIC_B200_SIMT_CHECK", None)
+    r = subprocess.run([sys.executable, "-c", "import cpic_b200._lib as L; L.lib()"], cwd=ROOT, env=env,
+                       capture_output=True, text=True)
+    assert r.returncode != 0 and "no CPU path" in r.stderr, r.stderr[-500:]
+
+
 def test_kernel_parity_suite_under_the_interpreter(simt_build):
     """tests/test_gpu_parity.py, every case: solver, stage_field_E, deposit, the first 10 steps of
     seven configurations staged and fused, bitwise fused == staged, determinism, hot beam, velocity
