@@ -289,41 +289,72 @@ k_field_E(const double *__restrict__ phi, double *__restrict__ Ex, double *__res
 	Ex[(size_t) iy * g.SE + ix] = ex;
 }
 
+/* k_phi_finish and k_field_E in one pass (one rank: the phi ghost rows are images of the slab's
+ * own rows, so nothing has to travel in between). Thread (c, r) writes phi[r][c] and, for r <= ny,
+ * E at (c, r) from the same normalised values k_phi_finish would have stored: raw / N first, then
+ * the differences -- bit for bit what the two kernels produce. */
+static __global__ void
+k_phi_E(const double *__restrict__ raw, double *__restrict__ phi, double *__restrict__ Ex,
+		double *__restrict__ Ey, Geom g, double N)
+{
+	const int c = blockIdx.x * blockDim.x + threadIdx.x;
+	const int r = blockIdx.y;               /* row of the ny+3 row phi array */
+	/* slab row behind array row q: 0 <- ny-1, 1..ny <- 0..ny-1, ny+1, ny+2 <- 0, 1 */
+	auto src = [&](int q) { return q >= 1 && q <= g.ny ? q - 1 : q == 0 ? g.ny - 1 : q - 1 - g.ny; };
+	auto val = [&](int q, int col) { return raw[(size_t) src(q) * g.S + col] / N; };      /* col < nx */
+	if(c < g.S)
+	{
+		double v = raw[(size_t) src(r) * g.S + c];
+		if(c < g.nx) v /= N;
+		phi[(size_t) r * g.S + c] = v;
+	}
+	if(r <= g.ny && c < g.SE)
+	{
+		const int iy = r, cc = c % g.nx;
+		const int x0 = cc == 0 ? g.nx - 1 : cc - 1;
+		const int x1 = cc == g.nx - 1 ? 0 : cc + 1;
+		const double dx2 = 2 * g.dx, dy2 = 2 * g.dy;
+		/* slab row iy is array row iy+1: north neighbour array row iy, south iy+2 */
+		Ey[(size_t) iy * g.SE + c] = (val(iy, cc) - val(iy + 2, cc)) / dy2;
+		Ex[(size_t) iy * g.SE + c] = (val(iy + 1, x0) - val(iy + 1, x1)) / dx2;
+	}
+}
+
 /* Second half of the deposition: adds, in a fixed order, the halo sums that the CTAs of
  * k_deposit left in hb (bottom rows), hr (right columns) and hc (corners) to the nodes
  * they belong to. Row ny (the south ghost row of `_rho`) is owned by nobody and is
- * assembled here from scratch. Grid: (ceil(nx/128), nby) -- rows y = (by+1)*BY. */
+ * assembled here from scratch. Grid rows [0, nby) are the block-row boundaries y = (by+1)*BY,
+ * grid rows [nby, nby + ncx) the CTA-column boundaries for the rows the first job does not
+ * visit; the two jobs write disjoint nodes and read only their own. */
 static __global__ void
-k_stitch_rows(double *__restrict__ rho, const double *__restrict__ hb,
-		const double *__restrict__ hr, const double *__restrict__ hc, Geom g)
+k_stitch(double *__restrict__ rho, const double *__restrict__ hb, const double *__restrict__ hr,
+		const double *__restrict__ hc, Geom g)
 {
-	int x = blockIdx.x * blockDim.x + threadIdx.x;
-	int by = blockIdx.y + 1;          /* 1 .. nby */
-	if(x >= g.nx) return;
-	int y = by * g.BY;
-	int W = g.WPC * g.BX, ncx = g.nbx / g.WPC;
-	double v = y < g.ny ? rho[(size_t) y * g.S + x] : 0.0;
-	v += hb[(size_t) (by - 1) * g.nx + x];
-	if(x % W == 0)
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	const int W = g.WPC * g.BX, ncx = g.nbx / g.WPC;
+	if((int) blockIdx.y < g.nby)
 	{
-		int left = (x / W + ncx - 1) % ncx;
-		if(y < g.ny) v += hr[(size_t) left * g.ny + y];
-		v += hc[(size_t) (by - 1) * ncx + left];
+		const int x = t, by = blockIdx.y + 1;          /* 1 .. nby */
+		if(x >= g.nx) return;
+		const int y = by * g.BY;
+		double v = y < g.ny ? rho[(size_t) y * g.S + x] : 0.0;
+		v += hb[(size_t) (by - 1) * g.nx + x];
+		if(x % W == 0)
+		{
+			const int left = (x / W + ncx - 1) % ncx;
+			if(y < g.ny) v += hr[(size_t) left * g.ny + y];
+			v += hc[(size_t) (by - 1) * ncx + left];
+		}
+		rho[(size_t) y * g.S + x] = v;
 	}
-	rho[(size_t) y * g.S + x] = v;
-}
-
-/* Right-column halos for the rows k_stitch_rows does not visit. Grid: (ceil(ny/128), ncx) */
-static __global__ void
-k_stitch_cols(double *__restrict__ rho, const double *__restrict__ hr, Geom g)
-{
-	int y = blockIdx.x * blockDim.x + threadIdx.x;
-	int cx = blockIdx.y;
-	if(y >= g.ny) return;
-	if(y % g.BY == 0 && y > 0) return;
-	int W = g.WPC * g.BX, ncx = g.nbx / g.WPC;
-	int left = (cx + ncx - 1) % ncx;
-	rho[(size_t) y * g.S + (size_t) cx * W] += hr[(size_t) left * g.ny + y];
+	else
+	{
+		const int y = t, cx = blockIdx.y - g.nby;
+		if(y >= g.ny) return;
+		if(y % g.BY == 0 && y > 0) return;
+		const int left = (cx + ncx - 1) % ncx;
+		rho[(size_t) y * g.S + (size_t) cx * W] += hr[(size_t) left * g.ny + y];
+	}
 }
 
 /* Single rank: the ghost row goes to ourselves and is added to row 0

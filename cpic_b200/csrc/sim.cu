@@ -1005,9 +1005,16 @@ cpic_b200_stage_field_E(cpic_b200_sim_t *s)
 	dim3 grid((g.S + 127) / 128, g.ny + 3);
 	/* N is an int in the reference (src/solver.c:366, :494) */
 	const double N = (double) (int) ((long long) g.nx * g.ny_glob);
-	k_phi_finish<<<grid, 128, 0, s->stream>>>(s->phi_raw, s->phi, g, N, s->comm ? 0 : 1);
+	if(!s->comm)
+	{
+		/* one rank: normalisation, ghost rows and the differences in one pass */
+		dim3 gridPE((std::max(g.S, g.SE) + 127) / 128, g.ny + 3);
+		k_phi_E<<<gridPE, 128, 0, s->stream>>>(s->phi_raw, s->phi, s->Ex, s->Ey, g, N);
+		return check_launch(s);
+	}
+	k_phi_finish<<<grid, 128, 0, s->stream>>>(s->phi_raw, s->phi, g, N, 0);
 	if((rc = check_launch(s))) return rc;
-	if(s->comm && (rc = comm_phi_halo(s->comm, s->phi, s->stream))) return rc;
+	if((rc = comm_phi_halo(s->comm, s->phi, s->stream))) return rc;
 	dim3 gridE((g.SE + 127) / 128, g.ny + 1);
 	k_field_E<<<gridE, 128, 0, s->stream>>>(s->phi, s->Ex, s->Ey, g);
 	return check_launch(s);
@@ -1210,9 +1217,8 @@ cpic_b200_stage_field_rho(cpic_b200_sim_t *s)
 	}
 	else
 	{
-		k_stitch_rows<<<dim3((g.nx + 127) / 128, g.nby), 128, 0, s->stream>>>(s->rho, s->hb, s->hr, s->hc, g);
-		k_stitch_cols<<<dim3((g.ny + 127) / 128, ncx), 128, 0, s->stream>>>(s->rho, s->hr, g);
-		int rc = check_launch(s, 2);
+		k_stitch<<<dim3((std::max(g.nx, g.ny) + 127) / 128, g.nby + ncx), 128, 0, s->stream>>>(s->rho, s->hb, s->hr, s->hc, g);
+		int rc = check_launch(s);
 		if(rc) return rc;
 	}
 	/* comm_send_ghost_rho / comm_recv_ghost_rho, reference src/comm_field.c:51-136 */
