@@ -1106,8 +1106,16 @@ struct DepositSet {
 	int n;
 };
 
+/* -DDEP_MIN_CTAS=5 asks for 5 resident CTAs per SM (46 registers, no spills, against 60 and 4 CTAs):
+ * 16384 blocks are then 2.77 waves instead of 3.46. To be measured. */
+#ifdef DEP_MIN_CTAS
+#define DEP_BOUNDS __launch_bounds__(32 * MAX_WPC, DEP_MIN_CTAS)
+#else
+#define DEP_BOUNDS __launch_bounds__(32 * MAX_WPC)
+#endif
+
 template <bool FIRST>
-__global__ void __launch_bounds__(32 * MAX_WPC)
+__global__ void DEP_BOUNDS
 k_deposit(const __grid_constant__ DepositSet set, Geom g, int nb,
 		double *__restrict__ rho, double *__restrict__ hb, double *__restrict__ hr,
 		double *__restrict__ hc)
