@@ -1106,13 +1106,14 @@ struct DepositSet {
 	int n;
 };
 
-/* -DDEP_MIN_CTAS=5 asks for 5 resident CTAs per SM (46 registers, no spills, against 60 and 4 CTAs):
- * 16384 blocks are then 2.77 waves instead of 3.46. To be measured. */
-#ifdef DEP_MIN_CTAS
-#define DEP_BOUNDS __launch_bounds__(32 * MAX_WPC, DEP_MIN_CTAS)
-#else
-#define DEP_BOUNDS __launch_bounds__(32 * MAX_WPC)
+/* Resident CTAs per SM the deposit is compiled for. 4: 64 registers, no spills -- the occupancy of
+ * the build measured in round 1. -DDEP_MIN_CTAS=5: 46 registers, no spills; 16384 blocks are then
+ * 2.77 waves instead of 3.46 (to be measured). Without a bound ptxas settles on 48 registers and
+ * a 4-byte spill. */
+#ifndef DEP_MIN_CTAS
+#define DEP_MIN_CTAS 4
 #endif
+#define DEP_BOUNDS __launch_bounds__(32 * MAX_WPC, DEP_MIN_CTAS)
 
 template <bool FIRST>
 __global__ void DEP_BOUNDS
