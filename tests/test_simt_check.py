@@ -119,6 +119,14 @@ def test_reference_drivers_through_the_dropin_under_the_interpreter(simt_build):
     run_under_interpreter(simt_build, ["tests/test_gpu_dropin.py", "-k", "cyclotron or cli_and_output"])
 
 
+def test_bench_call_sequence_under_the_interpreter(simt_build):
+    """tests/simt/bench_sequence.py: every C-ABI call bench.py makes, in its order, at a small size."""
+    env = dict(os.environ, CPIC_B200_LIB=simt_build, CPIC_B200_SIMT_CHECK="1")
+    r = subprocess.run([sys.executable, os.path.join(SIMT, "bench_sequence.py")], cwd=ROOT, env=env,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "DRY RUN OK" in r.stdout, (r.stdout + r.stderr)[-3000:]
+
+
 def test_physics_under_the_interpreter(simt_build):
     """Two-stream growth rate and energy history, constant speed and cyclotron orbits (the 1200-step
     harmonic golden trajectory is left to the GPU run: minutes of interpretation)."""
