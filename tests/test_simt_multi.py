@@ -62,3 +62,11 @@ def test_capacity_growth_is_agreed_between_ranks_on_cpu(simt_build):
 def test_streamed_initialisation_on_two_ranks_on_cpu(simt_build):
     run_ranks_cpu(simt_build, 2, "2d-2species-small.conf", 6, env={"MGPU_STREAMED": "1000"})
 
+
+def test_run_and_run_timed_on_two_ranks_on_cpu(simt_build):
+    """cpic_b200_run / cpic_b200_run_timed as bench.py calls them with several ranks: 70 steps, so that
+    the collective capacity check inside the library (every 32 steps) runs twice, with tight
+    capacities so that it has something to agree on."""
+    out = run_ranks_cpu(simt_build, 2, "uniform-small.conf", 70, env={"MGPU_RUN": "1", "MGPU_TIGHT": "1"}, timeout=900)
+    assert "MGPU-CAPS" in out
+
