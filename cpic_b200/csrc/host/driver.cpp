@@ -206,17 +206,19 @@ cpic_b200_main(int argc, char **argv)
 		const double t = now() - t1;
 		if(run.stop_SEM > 0.0)
 		{
-			/* sampling_complete, src/sim.c:440-479 */
-			const double std = n > 1 ? sqrt(m2 / (double) (n - 1)) : 0.0;
-			const double sem = n > 0 ? std / sqrt((double) n) : 0.0;
+			/* sampling_complete, src/sim.c:440-479: perf_stats BEFORE perf_record -- the mean, std and
+			 * sem that are printed and tested are those of the samples before this one */
+			const double mean0 = mean;
+			const double std = n >= 2 ? sqrt(m2 / (double) (n - 1)) : 0.0;
+			const double sem = n >= 2 ? std / sqrt((double) n) : 0.0;
+			const double rsem = mean0 != 0.0 ? sem / mean0 : sem;
+			/* perf_record, src/perf.c:85-108 (Welford) */
 			n++;
-			const double d = t - mean;
-			mean += d / (double) n;
-			m2 += d * (t - mean);
-			const double rsem = mean != 0.0 ? sem / mean : sem;
+			mean = mean0 + (t - mean0) / (double) n;
+			m2 += (t - mean0) * (t - mean);
 			printf("stats iter=%ld last=%e mean=%e std=%e sem=%e rsem=%e mem=%ld solver=%e\n",
-					(long) cpic_b200_iter(sim) - 1, t, mean, std, sem, rsem, 0L, 0.0);
-			if(cpic_b200_iter(sim) - 1 >= 30 && 1.96 * sem < run.stop_SEM * mean)
+					(long) cpic_b200_iter(sim) - 1, t, mean0, std, sem, rsem, 0L, 0.0);
+			if(cpic_b200_iter(sim) - 1 >= 30 && 1.96 * sem < run.stop_SEM * mean0)
 			{
 				printf("sampling complete\n");
 				running = 0;

@@ -320,46 +320,8 @@ k_phi_E(const double *__restrict__ raw, double *__restrict__ phi, double *__rest
 	}
 }
 
-/* Second half of the deposition: adds, in a fixed order, the halo sums that the CTAs of
- * k_deposit left in hb (bottom rows), hr (right columns) and hc (corners) to the nodes
- * they belong to. Row ny (the south ghost row of `_rho`) is owned by nobody and is
- * assembled here from scratch. Grid rows [0, nby) are the block-row boundaries y = (by+1)*BY,
- * grid rows [nby, nby + ncx) the CTA-column boundaries for the rows the first job does not
- * visit; the two jobs write disjoint nodes and read only their own. */
-static __global__ void
-k_stitch(double *__restrict__ rho, const double *__restrict__ hb, const double *__restrict__ hr,
-		const double *__restrict__ hc, Geom g)
-{
-	const int t = blockIdx.x * blockDim.x + threadIdx.x;
-	const int W = g.WPC * g.BX, ncx = g.nbx / g.WPC;
-	if((int) blockIdx.y < g.nby)
-	{
-		const int x = t, by = blockIdx.y + 1;          /* 1 .. nby */
-		if(x >= g.nx) return;
-		const int y = by * g.BY;
-		double v = y < g.ny ? rho[(size_t) y * g.S + x] : 0.0;
-		v += hb[(size_t) (by - 1) * g.nx + x];
-		if(x % W == 0)
-		{
-			const int left = (x / W + ncx - 1) % ncx;
-			if(y < g.ny) v += hr[(size_t) left * g.ny + y];
-			v += hc[(size_t) (by - 1) * ncx + left];
-		}
-		rho[(size_t) y * g.S + x] = v;
-	}
-	else
-	{
-		const int y = t, cx = blockIdx.y - g.nby;
-		if(y >= g.ny) return;
-		if(y % g.BY == 0 && y > 0) return;
-		const int left = (cx + ncx - 1) % ncx;
-		rho[(size_t) y * g.S + (size_t) cx * W] += hr[(size_t) left * g.ny + y];
-	}
-}
-
-/* Single rank: the ghost row goes to ourselves and is added to row 0
- * (reference src/comm_field.c:51-136). With several ranks `recv` is the row received
- * from rank-1. */
+/* comm_recv_ghost_rho, reference src/comm_field.c:99-136: the ghost row received from rank-1
+ * is added to row 0 (on one rank k_rho_assemble folds the own ghost row on its way). */
 static __global__ void
 k_rho_fold(double *__restrict__ rho, const double *__restrict__ recv, Geom g)
 {
@@ -1071,23 +1033,32 @@ k_absorb(SpeciesDev sp, Geom g, int nb, int arr, int *__restrict__ errflag)
 }
 
 /* interpolate_p2f_rho, reference src/interpolate.c:282-346 / :161-276, accumulate-correct.
- * Each warp sums its block's particles -- species after species, own segment, then the
- * arrivals pending in the outbox -- into private accumulators in shared memory: DEP_REP
- * replicas (lane l uses replica l % DEP_REP) of four arrays indexed by CELL, one per corner
- * weight (w00, w01, w10, w11). Two lanes can then only meet when they hold particles of the
- * same cell in the same replica; such lanes are found with ballots, the first of them adds up
- * the group's contributions in lane order (shuffles) and alone updates the accumulators --
- * plain read-modify-write, race free, four independent updates per lane. Every accumulator
- * therefore has a fixed order of additions (species, batch, lane). The CTA finally forms every node of its tile as the fixed-order sum of the (up to
- * four) cells around it, replicas in order, left block before right block, and stores:
- * interior nodes to rho (`=` when FIRST, `+=` otherwise), bottom row / right column / corner
- * to the halo arrays that k_stitch_* add in a fixed order. rho_reset (src/field.c:163-210)
- * is implicit. One launch takes every species (DEP_FUSED), so that a block's accumulators
- * are cleared, merged and stored once per step instead of once per species. */
-#define DEP_REP 2
+ *
+ * k_deposit: one warp sums one particle block at a time -- species after species, own segment,
+ * then the arrivals pending in the outbox -- into private accumulators in shared memory,
+ * indexed by NODE of the block's (BX+1) x (BY+1) tile and replicated in `ncol` COLUMNS (16 when
+ * the tile allows): lane l adds to column l % ncol of the four nodes around its particle.
+ * A column is 8 bytes wide and the columns of a node are adjacent, so the 16 lanes of a
+ * half-warp hit 16 different bank pairs whatever cells their particles sit in: every
+ * shared-memory access of the accumulation is conflict free (one wavefront per half-warp), and
+ * no two lanes of a half-warp share an address. Lanes l and l + ncol do share a column: the
+ * 32 / ncol groups take turns (warp barrier in between). No votes, no shuffles, no atomics;
+ * every accumulator has a fixed order of additions (species, batch, group, the lane's two
+ * particles), and the columns of a node are added up in a fixed (rotated, again conflict-free)
+ * order. The node sums of the block go to `tiles` (block-major); warps are independent of each
+ * other (no CTA barrier, blocks handed out round-robin to a persistent grid), and a block's sums
+ * do not depend on which warp formed them.
+ *
+ * k_rho_assemble: every node of the slab from the (up to four) block tiles that share it, in a
+ * fixed order; rho_reset (src/field.c:163-210) is implicit, and on one rank the ghost row is
+ * folded into row 0 on the way (src/comm_field.c:51-136: the send to oneself). */
 #define DEP_MAX_SPECIES 8
+#define DEP_MAX_COLS 16
 #ifndef DEP_FUSED
 #define DEP_FUSED 1
+#endif
+#ifndef DEP_WARPS
+#define DEP_WARPS 4              /* warps per CTA: shared memory per CTA = DEP_WARPS tiles */
 #endif
 
 /* What the deposit reads of one species */
@@ -1106,166 +1077,160 @@ struct DepositSet {
 	int n;
 };
 
-/* Resident CTAs per SM the deposit is compiled for. 4: 64 registers, no spills -- the occupancy of
- * the build measured in round 1. -DDEP_MIN_CTAS=5: 46 registers, no spills; 16384 blocks are then
- * 2.77 waves instead of 3.46 (to be measured). Without a bound ptxas settles on 48 registers and
- * a 4-byte spill. */
-#ifndef DEP_MIN_CTAS
-#define DEP_MIN_CTAS 4
-#endif
-#define DEP_BOUNDS __launch_bounds__(32 * MAX_WPC, DEP_MIN_CTAS)
+/* Weights and first accumulator of a particle, then the lane's turn at the accumulators */
+struct DepContribution {
+	double a00, a01, a10, a11;
+	int n0;                  /* accumulator of node (lx, ly), this lane's column; -1: no particle */
+};
+
+__device__ __forceinline__ DepContribution
+dep_contribution(const Geom &g, double x, double y, double vq, bool valid, int cx0, int cy0, int NW, int ncol, int col)
+{
+	DepContribution c;
+	int i0x, i0y;
+	double w00, w01, w10, w11;
+	cic_weights(g, x, y, i0x, i0y, w00, w01, w10, w11);
+	c.a00 = MUL(w00, vq); c.a01 = MUL(w01, vq); c.a10 = MUL(w10, vq); c.a11 = MUL(w11, vq);
+	c.n0 = valid ? ((i0y - cy0) * NW + (i0x - cx0)) * ncol + col : -1;
+	return c;
+}
+
+/* corners: 00 = (x, y), 10 = (x+1, y), 01 = (x, y+1), 11 = (x+1, y+1) */
+__device__ __forceinline__ void
+dep_add(double *t, const DepContribution &c, int ncol, int rowstep)
+{
+	if(c.n0 < 0) return;
+	double *q0 = t + c.n0, *q1 = q0 + rowstep;
+	const double v00 = q0[0], v10 = q0[ncol], v01 = q1[0], v11 = q1[ncol];
+	q0[0] = ADD(v00, c.a00);
+	q0[ncol] = ADD(v10, c.a10);
+	q1[0] = ADD(v01, c.a01);
+	q1[ncol] = ADD(v11, c.a11);
+}
 
 template <bool FIRST>
-__global__ void DEP_BOUNDS
-k_deposit(const __grid_constant__ DepositSet set, Geom g, int nb,
-		double *__restrict__ rho, double *__restrict__ hb, double *__restrict__ hr,
-		double *__restrict__ hc)
+__global__ void __launch_bounds__(32 * DEP_WARPS)
+k_deposit(const __grid_constant__ DepositSet set, Geom g, int nb, int ncol, double *__restrict__ tiles)
 {
 	extern __shared__ __align__(128) unsigned char smem[];
-	double *acc = (double *) smem;
-	const int NC = g.BX * g.BY;                  /* cells per block */
-	const int wsz = DEP_REP * 4 * NC;            /* accumulators per warp: [replica][corner][cell] */
-
+	const int NW = g.BX + 1;                     /* nodes per tile row */
+	const int NN = NW * (g.BY + 1);              /* nodes per block tile */
+	const int wsz = NN * ncol;                   /* accumulators per warp: [node][column] */
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const unsigned lt = (1u << lane) - 1;
-	const int ncx = g.nbx / g.WPC;
-	const int by = blockIdx.x / ncx, cx = blockIdx.x % ncx;
-	const int bx = cx * g.WPC + warp;
-	const int b = by * g.nbx + bx;
-	double *t = acc + warp * wsz + (lane % DEP_REP) * 4 * NC;
-	const int cx0 = bx * g.BX, cy0 = by * g.BY;
-	const int cbits = g.lBX + g.lBY;             /* bits of a cell index */
-	static_assert(DEP_REP == 1 || DEP_REP == 2, "replica masks are written for one or two replicas");
-	const unsigned repmask = DEP_REP == 1 ? FULL : 0x55555555u << (lane & 1);   /* the lanes of my replica */
+	double *t = (double *) smem + warp * wsz;
+	const int col = lane & (ncol - 1), grp = lane / ncol, ngrp = 32 / ncol;
+	const int rowstep = NW * ncol;
+	__shared__ int scratch_[DEP_WARPS][20];
+	int *scratch = scratch_[warp];
 
-	__shared__ int scratch[MAX_WPC][18];
-
-	for(int k = lane; k < wsz; k += 32) acc[warp * wsz + k] = 0.0;
-	__syncwarp();
-
-	for(int is = 0; is < set.n; is++)
+	for(int b = blockIdx.x * DEP_WARPS + warp; b < nb; b += gridDim.x * DEP_WARPS)
 	{
-		const DepositSpecies &sp = set.s[is];
-		const double *__restrict__ sx = sp.x, *__restrict__ sy = sp.y;
-		const double *__restrict__ arec = sp.arec;
-		const double vq = sp.vq;
-		__syncwarp();                /* the previous species' run table is no longer read */
-		const Arrivals A = find_arrivals(sp.acount, sp.nob, g, nb, b, lane, scratch[warp]);
-		const int cnt = sp.count[b];
-		const int T = cnt + A.total;
+		const int bx = b % g.nbx, by = b / g.nbx;
+		const int cx0 = bx * g.BX, cy0 = by * g.BY;
+		for(int k = lane; k < wsz; k += 32) t[k] = 0.0;
+		__syncwarp();
 
-		double px = 0, py = 0;
-		if(lane < T)
+		for(int is = 0; is < set.n; is++)
 		{
-			if(lane < cnt) { px = sx[seg_slot(sp.cap, b, lane)]; py = sy[seg_slot(sp.cap, b, lane)]; }
-			else
-			{
-				const double2 v = *(const double2 *) (arec + (size_t) arrival_slot(A, sp.roff, sp.rcap, lane - cnt) * OREC);
-				px = v.x; py = v.y;
-			}
-		}
-
-		for(int i0 = 0; i0 < T; i0 += 32)
-		{
-			const int i = i0 + lane;
-			const bool valid = i < T;
-			const double x = px, y = py;
-			if(i + 32 < T)
-			{
-				if(i + 32 < cnt) { px = sx[seg_slot(sp.cap, b, i + 32)]; py = sy[seg_slot(sp.cap, b, i + 32)]; }
-				else
-				{
-					const double2 v = *(const double2 *) (arec + (size_t) arrival_slot(A, sp.roff, sp.rcap, i + 32 - cnt) * OREC);
-					px = v.x; py = v.y;
-				}
-			}
-
-			int cell = 0;
-			double a00 = 0, a01 = 0, a10 = 0, a11 = 0;
-			if(valid)
-			{
-				int i0x, i0y;
-				double w00, w01, w10, w11;
-				cic_weights(g, x, y, i0x, i0y, w00, w01, w10, w11);
-				a00 = MUL(w00, vq); a01 = MUL(w01, vq); a10 = MUL(w10, vq); a11 = MUL(w11, vq);
-				cell = ((i0y - cy0) << g.lBX) + (i0x - cx0);
-			}
-			/* lanes of my replica that hold a particle of my cell: one ballot per bit of the cell
-			 * index (MATCH.ANY is an order of magnitude slower than the handful of votes) */
-			unsigned peers = __ballot_sync(FULL, valid) & repmask;
-			for(int k = 0; k < cbits; k++)
-			{
-				const unsigned bk = __ballot_sync(FULL, (cell >> k) & 1);
-				peers &= ((cell >> k) & 1) ? bk : ~bk;
-			}
-			const bool lead = valid && (peers & lt) == 0;
-			const int members = __reduce_max_sync(FULL, valid ? __popc(peers) : 0);
-			/* the first lane of every group collects the others' contributions in lane order and
-			 * is the only one to touch the accumulators: one read-modify-write round per batch */
-			unsigned rest = lead ? peers & ~(1u << lane) : 0u;
-			for(int r = 1; r < members; r++)
-			{
-				const int src = rest ? __ffs((int) rest) - 1 : lane;
-				const double b00 = __shfl_sync(FULL, a00, src), b01 = __shfl_sync(FULL, a01, src);
-				const double b10 = __shfl_sync(FULL, a10, src), b11 = __shfl_sync(FULL, a11, src);
-				if(rest)
-				{
-					a00 = ADD(a00, b00); a01 = ADD(a01, b01); a10 = ADD(a10, b10); a11 = ADD(a11, b11);
-					rest &= rest - 1;
-				}
-			}
-			if(lead)
-			{
-				const double v0 = t[cell], v1 = t[NC + cell], v2 = t[2 * NC + cell], v3 = t[3 * NC + cell];
-				t[cell] = ADD(v0, a00);
-				t[NC + cell] = ADD(v1, a01);
-				t[2 * NC + cell] = ADD(v2, a10);
-				t[3 * NC + cell] = ADD(v3, a11);
-			}
+			const DepositSpecies &sp = set.s[is];
+			const double vq = sp.vq;
+			const int cnt = sp.count[b];
+			const double *__restrict__ sx = sp.x + seg_slot(sp.cap, b, 0);
+			const double *__restrict__ sy = sp.y + seg_slot(sp.cap, b, 0);
+#if SEG_AOSOA
+#error "k_deposit walks plain segments"
+#endif
+			/* own segment: two particles per lane and turn, the next two already on their way */
+			int k = lane;
+			double xa = 0, ya = 0, xb = 0, yb = 0;
+			if(k < cnt) { xa = sx[k]; ya = sy[k]; }
+			if(k + 32 < cnt) { xb = sx[k + 32]; yb = sy[k + 32]; }
+			/* the arrival counters travel while the segment is walked */
 			__syncwarp();
-		}
-	}
-
-	__syncthreads();
-
-	/* every node of the CTA tile from the cells around it. Block-local node (lr, lc), lr in
-	 * [0, BY], lc in [0, BX]: corner (a, b) of cell (lc - a, lr - b) when that cell exists;
-	 * corner arrays: 0 = w00 (0,0), 1 = w01 (0,+1), 2 = w10 (+1,0), 3 = w11 (+1,+1). */
-	const int W = g.WPC * g.BX, THd = g.BY + 1;
-	for(int k = threadIdx.x; k < THd * (W + 1); k += blockDim.x)
-	{
-		const int r = k / (W + 1), c = k % (W + 1);
-		double v = 0.0;
-		/* the block whose column range holds c contributes its left corners (a = 0); the block
-		 * to the left contributes its right corners (a = 1) */
-#pragma unroll
-		for(int side = 0; side < 2; side++)
-		{
-			const int a = side == 0 ? 1 : 0;                       /* left block first */
-			const int w = (c - a) >= 0 ? (c - a) >> g.lBX : -1;
-			if(w < 0 || w >= g.WPC) continue;
-			const int lx = (c - a) - (w << g.lBX);
-			const double *tw = acc + w * wsz;
-#pragma unroll
-			for(int bb = 0; bb < 2; bb++)
+			const Arrivals A = find_arrivals(sp.acount, sp.nob, g, nb, b, lane, scratch);
+			for(; k - lane < cnt; k += 64)
 			{
-				const int ly = r - bb;
-				if(ly < 0 || ly >= g.BY) continue;
-				const int cell = (ly << g.lBX) + lx;
-				const int corner = a * 2 + bb;
-#pragma unroll
-				for(int rep = 0; rep < DEP_REP; rep++)
-					v = ADD(v, tw[rep * 4 * NC + corner * NC + cell]);
+				double nxa = 0, nya = 0, nxb = 0, nyb = 0;
+				if(k + 64 < cnt) { nxa = sx[k + 64]; nya = sy[k + 64]; }
+				if(k + 96 < cnt) { nxb = sx[k + 96]; nyb = sy[k + 96]; }
+				const DepContribution ca = dep_contribution(g, xa, ya, vq, k < cnt, cx0, cy0, NW, ncol, col);
+				const DepContribution cb = dep_contribution(g, xb, yb, vq, k + 32 < cnt, cx0, cy0, NW, ncol, col);
+				for(int p = 0; p < ngrp; p++)
+				{
+					if(grp == p) { dep_add(t, ca, ncol, rowstep); dep_add(t, cb, ncol, rowstep); }
+					__syncwarp();
+				}
+				xa = nxa; ya = nya; xb = nxb; yb = nyb;
+			}
+			/* arrivals: (x, y) are the first 16 bytes of a 48-byte record */
+			int f = lane;
+			double2 v = make_double2(0.0, 0.0);
+			if(f < A.total) v = *(const double2 *) (sp.arec + (size_t) arrival_slot(A, sp.roff, sp.rcap, f) * OREC);
+			for(; f - lane < A.total; f += 32)
+			{
+				double2 nv = make_double2(0.0, 0.0);
+				if(f + 32 < A.total) nv = *(const double2 *) (sp.arec + (size_t) arrival_slot(A, sp.roff, sp.rcap, f + 32) * OREC);
+				const DepContribution ca = dep_contribution(g, v.x, v.y, vq, f < A.total, cx0, cy0, NW, ncol, col);
+				for(int p = 0; p < ngrp; p++)
+				{
+					if(grp == p) dep_add(t, ca, ncol, rowstep);
+					__syncwarp();
+				}
+				v = nv;
 			}
 		}
-		double *dst;
-		if(r < g.BY && c < W) dst = rho + (size_t) (by * g.BY + r) * g.S + (size_t) cx * W + c;
-		else if(r == g.BY && c < W) dst = hb + (size_t) by * g.nx + (size_t) cx * W + c;
-		else if(r < g.BY) dst = hr + (size_t) cx * g.ny + by * g.BY + r;
-		else dst = hc + (size_t) by * ncx + cx;
-		if(FIRST) *dst = v;
-		else *dst += v;
+
+		/* the columns of every node, in a fixed order that starts at a different column for
+		 * neighbouring nodes (conflict-free reads) */
+		double *out = tiles + (size_t) b * NN;
+		for(int n = lane; n < NN; n += 32)
+		{
+			const double *q = t + n * ncol;
+			double s = 0.0;
+			for(int k = 0; k < ncol; k++) s = ADD(s, q[(k + n) & (ncol - 1)]);
+			if(FIRST) out[n] = s;
+			else out[n] += s;
+		}
+		__syncwarp();
 	}
+}
+
+/* Grid node (x, y) of the slab, y in [0, ny] (row ny: the south ghost row of `_rho`), from the
+ * block tiles that hold it: the tile of block (x / BX, y / BY) at local node (x % BX, y % BY),
+ * and, on a block boundary, the right / bottom edge of the block before it (X periodic: node nx
+ * is node 0, src/interpolate.c:161-276). Order: upper left, upper right, lower left, lower right
+ * block. fold: row 0 also takes the ghost row (one rank). */
+static __global__ void
+k_rho_assemble(const double *__restrict__ tiles, double *__restrict__ rho, Geom g, int fold)
+{
+	const int x = blockIdx.x * blockDim.x + threadIdx.x;
+	const int y = blockIdx.y;                /* 0 .. ny */
+	if(x >= g.nx) return;
+	const int NW = g.BX + 1, NN = NW * (g.BY + 1);
+	auto node = [&](int yy)
+	{
+		const int bxr = x >> g.lBX, lx = x & (g.BX - 1);
+		const int bxl = lx == 0 ? (bxr == 0 ? g.nbx - 1 : bxr - 1) : -1;
+		const int byr = yy < g.ny ? yy >> g.lBY : -1, ly = yy & (g.BY - 1);
+		const int byl = (ly == 0 && yy > 0) ? (yy >> g.lBY) - 1 : -1;
+		double v = 0.0;
+		if(byl >= 0)
+		{
+			const double *tl = tiles + (size_t) byl * g.nbx * NN + g.BY * NW;
+			if(bxl >= 0) v = ADD(v, tl[(size_t) bxl * NN + g.BX]);
+			v = ADD(v, tl[(size_t) bxr * NN + lx]);
+		}
+		if(byr >= 0)
+		{
+			const double *tr = tiles + (size_t) byr * g.nbx * NN + ly * NW;
+			if(bxl >= 0) v = ADD(v, tr[(size_t) bxl * NN + g.BX]);
+			v = ADD(v, tr[(size_t) bxr * NN + lx]);
+		}
+		return v;
+	};
+	double v = node(y);
+	if(fold && y == 0) v = ADD(v, node(g.ny));
+	rho[(size_t) y * g.S + x] = v;
 }
 
 /* Compact image of a species for host round trips: the live particles of every block, block
@@ -1354,7 +1319,9 @@ k_sum(const double *__restrict__ in, int n, double *__restrict__ out)
 
 /* Throughput-only initialiser: particle k of block b sits uniformly inside block b, so
  * the plasma is uniform with equal block populations; u ~ U(-v, v) per axis as in the
- * reference's "random position" (src/particle.c:72-73). Counter-based (splitmix64). */
+ * reference's "random position" (src/particle.c:72-73), plus a drift (a beam: the
+ * "position delta" initialiser gives every particle the drift velocity, src/particle.c:152-153).
+ * Counter-based (splitmix64). */
 __device__ __forceinline__ double
 u01(uint64_t &s)
 {
@@ -1368,7 +1335,7 @@ u01(uint64_t &s)
 
 static __global__ void __launch_bounds__(256)
 k_init_uniform(SpeciesDev sp, Geom g, int nb, long long n, long long id0, double vx, double vy,
-		uint64_t seed)
+		double dux, double duy, uint64_t seed)
 {
 	const int lane = threadIdx.x & 31;
 	const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -1391,8 +1358,8 @@ k_init_uniform(SpeciesDev sp, Geom g, int nb, long long n, long long id0, double
 		const size_t ds = seg_slot(sp.cap, b, (int) k);
 		sp.x[ds] = x;
 		sp.y[ds] = y;
-		sp.ux[ds] = (2.0 * u01(s) - 1.0) * vx;
-		sp.uy[ds] = (2.0 * u01(s) - 1.0) * vy;
+		sp.ux[ds] = dux + (2.0 * u01(s) - 1.0) * vx;
+		sp.uy[ds] = duy + (2.0 * u01(s) - 1.0) * vy;
 		sp.uz[ds] = 0.0;
 		sp.id[ds] = gid;
 	}

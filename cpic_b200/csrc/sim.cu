@@ -86,7 +86,7 @@ struct cpic_b200_sim {
 	cufftDoubleComplex *gk;
 	cufftHandle plan_fwd, plan_inv;
 	bool have_plans;
-	double *hb, *hr, *hc;    /* deposit halos */
+	double *tiles;           /* deposit: node sums per particle block, nb x (BX+1)(BY+1) */
 	double *red;             /* reduction scratch */
 	double *img;             /* staging of the compact particle image */
 	long long *img_off;
@@ -95,6 +95,8 @@ struct cpic_b200_sim {
 	int *h_err;              /* pinned */
 	CUtensorMap mapEx, mapEy;
 	size_t smem_push, smem_dep;
+	int dep_cols;            /* accumulator columns per node of the deposit (kernels.cuh: k_deposit) */
+	int dep_ctas;            /* CTAs of the deposit that are resident at once on this device */
 
 	SpeciesHost sp[CPIC_B200_MAX_SPECIES];
 
@@ -153,6 +155,14 @@ tile_bytes(const Geom &g)
 {
 	size_t b = (size_t) g.TH * g.TW * sizeof(double);
 	return (b + 127) & ~(size_t) 127;
+}
+
+/* dynamic shared memory of k_gather_push<MODE>: header, scratch, two E tiles, per-warp rings */
+template <int MODE>
+static size_t
+push_smem_bytes(const cpic_b200_sim *s)
+{
+	return s->smem_push + (size_t) s->g.WPC * PIPE_STAGES * PipeArrays<MODE>::N * 32 * sizeof(double);
 }
 
 extern "C" int
@@ -264,10 +274,7 @@ cpic_b200_create(const cpic_b200_params_t *pp, cpic_b200_sim_t **out)
 	CKD(cudaMemset(s->phi_raw, 0, (size_t) g.ny * g.S * sizeof(double)));
 	CKD(cudaMemset(s->Ex, 0, (size_t) (g.ny + 1) * g.SE * sizeof(double)));
 	CKD(cudaMemset(s->Ey, 0, (size_t) (g.ny + 1) * g.SE * sizeof(double)));
-	const int ncx = g.nbx / g.WPC;
-	CKD(cudaMalloc(&s->hb, (size_t) g.nby * g.nx * sizeof(double)));
-	CKD(cudaMalloc(&s->hr, (size_t) ncx * g.ny * sizeof(double)));
-	CKD(cudaMalloc(&s->hc, (size_t) g.nby * ncx * sizeof(double)));
+	CKD(cudaMalloc(&s->tiles, (size_t) s->nb * (g.BX + 1) * (g.BY + 1) * sizeof(double)));
 	CKD(cudaMalloc(&s->red, ((size_t) std::max(s->nb, g.ny) + 16) * sizeof(double)));
 	/* [0] deferred error bits, [1 .. MAX_SPECIES] capacity requests (agreed over the ranks) */
 	CKD(cudaMalloc(&s->errflag, 16 * sizeof(int)));
@@ -309,7 +316,29 @@ cpic_b200_create(const cpic_b200_params_t *pp, cpic_b200_sim_t **out)
 	/* barrier + per-warp scratch + two E tiles + per-warp prefetch rings (sized for the
 	 * widest mode: 8 arrays) */
 	s->smem_push = PUSH_SMEM_HEADER + MAX_WPC * 32 * sizeof(int) + 2 * tile_bytes(g);
-	s->smem_dep = (size_t) g.WPC * DEP_REP * 4 * g.BX * g.BY * sizeof(double);
+	/* deposit: [warp of the CTA][node][column]; 16 columns when a few CTAs still fit an SM */
+	s->dep_cols = DEP_MAX_COLS;
+	if(getenv("CPIC_B200_DEP_COLS"))       /* experiments: 1, 2, 4, 8 or 16 */
+	{
+		const int c = atoi(getenv("CPIC_B200_DEP_COLS"));
+		if(c == 1 || c == 2 || c == 4 || c == 8 || c == 16) s->dep_cols = c;
+	}
+	while(s->dep_cols > 1 && (size_t) DEP_WARPS * (g.BX + 1) * (g.BY + 1) * s->dep_cols * sizeof(double) > 100 * 1024)
+		s->dep_cols >>= 1;
+	s->smem_dep = (size_t) DEP_WARPS * (g.BX + 1) * (g.BY + 1) * s->dep_cols * sizeof(double);
+	/* the opt-in shared-memory limits are per function AND per device: set them for this
+	 * simulation's device, whatever another simulation of the process did on another one */
+	CKD(cudaFuncSetAttribute(k_deposit<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) s->smem_dep));
+	CKD(cudaFuncSetAttribute(k_deposit<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) s->smem_dep));
+	{
+		int per_sm = 0, sms = 0;
+		CKD(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_deposit<true>, 32 * DEP_WARPS, s->smem_dep));
+		CKD(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+		s->dep_ctas = std::max(1, per_sm) * std::max(1, sms);
+	}
+	CKD(cudaFuncSetAttribute(k_gather_push<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) push_smem_bytes<0>(s)));
+	CKD(cudaFuncSetAttribute(k_gather_push<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) push_smem_bytes<1>(s)));
+	CKD(cudaFuncSetAttribute(k_gather_push<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) push_smem_bytes<2>(s)));
 
 	for(int i = 0; i < p.nspecies; i++) { s->sp[i].q = p.q[i]; s->sp[i].m = p.m[i]; }
 
@@ -346,7 +375,7 @@ cpic_b200_destroy(cpic_b200_sim_t *s)
 	if(s->comm) comm_destroy(s->comm);
 	if(s->have_plans) { cufftDestroy(s->plan_fwd); cufftDestroy(s->plan_inv); }
 	cudaFree(s->rho); cudaFree(s->phi); cudaFree(s->phi_raw); cudaFree(s->Ex); cudaFree(s->Ey);
-	cudaFree(s->G); cudaFree(s->gk); cudaFree(s->hb); cudaFree(s->hr); cudaFree(s->hc);
+	cudaFree(s->G); cudaFree(s->gk); cudaFree(s->tiles);
 	cudaFree(s->red); cudaFree(s->errflag); cudaFree(s->img); cudaFree(s->img_off);
 	if(s->h_err) cudaFreeHost(s->h_err);
 	if(s->ev[0]) cudaEventDestroy(s->ev[0]);
@@ -363,8 +392,26 @@ cpic_b200_destroy(cpic_b200_sim_t *s)
 static size_t
 align256(size_t v) { return (v + 255) & ~(size_t) 255; }
 
+/* Host lists may hold a particle exactly on the upper edge of the domain; the reference wraps it
+ * when it places the particles (particle_comm_initial -> periodic_boundary, src/comm_plasma.c:725-747:
+ * r >= L becomes r - L) */
+static inline double wrap_upper(double r, double L) { return r >= L ? r - L : r; }
+
+/* Several ranks: a particle is this rank's when its ROW is (the way every kernel and the slab filter
+ * of the front end place it); the row at the slab's upper edge belongs to the next rank, and y == Ly
+ * would have to be wrapped to rank 0 by the caller */
+static inline bool
+in_slab_rows(const Geom &g, double y)
+{
+	if(!(y >= 0.0 && y < g.Ly)) return false;
+	const int row = global_row(g, y);
+	return row >= g.row0 && row < g.row0 + g.ny;
+}
+
 static int ensure_particle_E(sim_t_ *s, int is);
 static int image_staging(sim_t_ *s, size_t doubles);
+
+static int alloc_species_storage(sim_t_ *s, int is, int cap);
 
 /* (Re)allocate one species with `cap` slots per block */
 static int
@@ -372,6 +419,24 @@ alloc_species(sim_t_ *s, int is, int cap)
 {
 	SpeciesHost &h = s->sp[is];
 	free_species(h);
+	/* sizes first: nothing is allocated when a limit is exceeded */
+	{
+		const double frac = s->p.outbox_fraction > 0 ? s->p.outbox_fraction : 0.3;
+		int ocs = (((int) ceil(cap * frac) + 31) / 32) * 32;
+		if(ocs < 32) ocs = 32;
+		const int occ = ((ocs / 4 + 31) / 32) * 32;
+		if((double) s->nb * cap >= 4294967296.0 || (double) s->nob * (4.0 * ocs + 4.0 * occ) >= 4294967296.0)
+			return fail(CPIC_B200_EINVAL, "species %d needs more than 2^32 particle slots on one GPU; lower capacity_factor / outbox_fraction or use more ranks", is);
+	}
+	int rc = alloc_species_storage(s, is, cap);
+	if(rc) free_species(h);      /* never leave a half-built species behind */
+	return rc;
+}
+
+static int
+alloc_species_storage(sim_t_ *s, int is, int cap)
+{
+	SpeciesHost &h = s->sp[is];
 	const size_t nslot = (size_t) s->nb * cap;
 	const size_t arr = align256(nslot * sizeof(double));
 	const size_t cnt = align256((size_t) s->nob * sizeof(int));
@@ -399,9 +464,6 @@ alloc_species(sim_t_ *s, int is, int cap)
 	h.d.ocs = ocs;
 	h.d.occ = occ;
 	h.d.nob = s->nob;
-	const double oslots = (double) s->nob * (4.0 * ocs + 4.0 * occ);
-	if((double) s->nb * cap >= 4294967296.0 || oslots >= 4294967296.0)
-		return fail(CPIC_B200_EINVAL, "species %d needs more than 2^32 particle slots on one GPU; lower capacity_factor / outbox_fraction or use more ranks", is);
 	unsigned off = 0;
 	for(int c = 0; c < 9; c++)
 	{
@@ -486,12 +548,14 @@ cpic_b200_set_particles(cpic_b200_sim_t *s, int is, int64_t n, const int64_t *id
 
 	std::vector<int> blk((size_t) n);
 	std::vector<int> cnt((size_t) s->nb, 0);
+	const bool one = s->p.nranks == 1;
 	for(int64_t i = 0; i < n; i++)
 	{
-		if(!(x[i] >= 0.0 && x[i] <= g.Lx) || !(y[i] >= g.y0 && y[i] <= y1))
-			return fail(CPIC_B200_EINVAL, "particle %lld at (%g, %g) is outside this rank's slab [0,%g]x[%g,%g]",
-					(long long) i, x[i], y[i], g.Lx, g.y0, y1);
-		int b = block_of(g, x[i], y[i]);
+		/* several ranks: the row at the slab's upper edge belongs to the next rank */
+		if(!(x[i] >= 0.0 && x[i] <= g.Lx) || !(one ? (y[i] >= 0.0 && y[i] <= y1) : in_slab_rows(g, y[i])))
+			return fail(CPIC_B200_EINVAL, "particle %lld at (%g, %g) is outside this rank's slab [0,%g]x[%g,%g%c",
+					(long long) i, x[i], y[i], g.Lx, g.y0, y1, one ? ']' : ')');
+		int b = block_of(g, wrap_upper(x[i], g.Lx), one ? wrap_upper(y[i], g.Ly) : y[i]);
 		blk[(size_t) i] = b;
 		cnt[(size_t) b]++;
 	}
@@ -520,7 +584,7 @@ cpic_b200_set_particles(cpic_b200_sim_t *s, int is, int64_t n, const int64_t *id
 	{
 		int b = blk[(size_t) i];
 		const size_t k = seg_slot(cap, b, fill[(size_t) b]++);
-		hseg[k] = x[i]; hseg[k + astep] = y[i];
+		hseg[k] = wrap_upper(x[i], g.Lx); hseg[k + astep] = one ? wrap_upper(y[i], g.Ly) : y[i];
 		hseg[k + 2 * astep] = ux[i]; hseg[k + 3 * astep] = uy[i]; hseg[k + 4 * astep] = uz ? uz[i] : 0.0;
 		const long long pid = id ? id[i] : i;
 		memcpy(&hseg[k + 5 * astep], &pid, sizeof(pid));
@@ -554,7 +618,8 @@ cpic_b200_count_particles(cpic_b200_sim_t *s, int is, int64_t n, const double *x
 		if(!(x[i] >= 0.0 && x[i] <= g.Lx) || !(y[i] >= 0.0 && y[i] <= g.Ly))
 			return fail(CPIC_B200_EINVAL, "species %d: particle %lld at (%g, %g) lies outside the domain", is,
 					(long long) i, x[i], y[i]);
-		const size_t b = (size_t) (global_row(g, y[i]) >> g.lBY) * (size_t) g.nbx + (size_t) (cell_ix(g, x[i]) >> g.lBX);
+		const size_t b = (size_t) (global_row(g, wrap_upper(y[i], g.Ly)) >> g.lBY) * (size_t) g.nbx
+			+ (size_t) (cell_ix(g, wrap_upper(x[i], g.Lx)) >> g.lBX);
 		(*h.tally)[b]++;
 	}
 	return 0;
@@ -598,10 +663,11 @@ cpic_b200_add_particles(cpic_b200_sim_t *s, int is, int64_t n, const int64_t *id
 	std::vector<int> blk((size_t) n), cnt((size_t) s->nb, 0), have((size_t) s->nb);
 	for(int64_t i = 0; i < n; i++)
 	{
-		if(!(x[i] >= 0.0 && x[i] <= g.Lx) || !(y[i] >= g.y0 && y[i] <= g.y0 + g.dy * g.ny))
+		const double y1 = g.y0 + g.dy * g.ny;
+		if(!(x[i] >= 0.0 && x[i] <= g.Lx) || !(s->p.nranks == 1 ? (y[i] >= 0.0 && y[i] <= y1) : in_slab_rows(g, y[i])))
 			return fail(CPIC_B200_EINVAL, "species %d: particle %lld at (%g, %g) lies outside this rank's slab", is,
 					(long long) i, x[i], y[i]);
-		const int b = block_of(g, x[i], y[i]);
+		const int b = block_of(g, wrap_upper(x[i], g.Lx), s->p.nranks == 1 ? wrap_upper(y[i], g.Ly) : y[i]);
 		blk[(size_t) i] = b;
 		cnt[(size_t) b]++;
 	}
@@ -622,7 +688,7 @@ cpic_b200_add_particles(cpic_b200_sim_t *s, int is, int64_t n, const int64_t *id
 	for(int64_t i = 0; i < n; i++)
 	{
 		const size_t k = (size_t) at[(size_t) blk[(size_t) i]]++;
-		img[k] = x[i]; img[(size_t) n + k] = y[i];
+		img[k] = wrap_upper(x[i], g.Lx); img[(size_t) n + k] = s->p.nranks == 1 ? wrap_upper(y[i], g.Ly) : y[i];
 		img[2 * (size_t) n + k] = ux[i]; img[3 * (size_t) n + k] = uy[i]; img[4 * (size_t) n + k] = uz ? uz[i] : 0.0;
 		memcpy(&img[5 * (size_t) n + k], &id[i], sizeof(int64_t));
 	}
@@ -642,6 +708,13 @@ cpic_b200_add_particles(cpic_b200_sim_t *s, int is, int64_t n, const int64_t *id
 extern "C" int
 cpic_b200_init_uniform(cpic_b200_sim_t *s, int is, int64_t n, int64_t id0, double vx, double vy, uint64_t seed)
 {
+	return cpic_b200_init_beam(s, is, n, id0, 0.0, 0.0, vx, vy, seed);
+}
+
+extern "C" int
+cpic_b200_init_beam(cpic_b200_sim_t *s, int is, int64_t n, int64_t id0, double dux, double duy,
+		double vx, double vy, uint64_t seed)
+{
 	if(!s || is < 0 || is >= s->p.nspecies || n < 0) return fail(CPIC_B200_EINVAL, "bad species or count");
 	CK(cudaSetDevice(s->device));
 	long long per = (n + s->nb - 1) / s->nb;
@@ -653,7 +726,7 @@ cpic_b200_init_uniform(cpic_b200_sim_t *s, int is, int64_t n, int64_t id0, doubl
 		int rc = alloc_species(s, is, cap);
 		if(rc) return rc;
 	}
-	k_init_uniform<<<(s->nb + 7) / 8, 256, 0, s->stream>>>(h.d, s->g, s->nb, n, id0, vx, vy, seed);
+	k_init_uniform<<<(s->nb + 7) / 8, 256, 0, s->stream>>>(h.d, s->g, s->nb, n, id0, vx, vy, dux, duy, seed);
 	CK(cudaGetLastError());
 	for(int k = 0; k < 2; k++) CK(cudaMemsetAsync(h.d.ob[k].count, 0, (size_t) s->nob * 9 * sizeof(int), s->stream));
 	h.n = n;
@@ -735,7 +808,13 @@ regrow(sim_t_ *s, int is, int newcap)
 	memset(&h.d, 0, sizeof(h.d));
 	int rc = alloc_species(s, is, newcap);
 	if(!rc && hadE && !h.d.pEx) rc = ensure_particle_E(s, is);
-	if(rc) return rc;
+	if(rc)
+	{
+		/* the species keeps its old storage (and the error of the failed allocation) */
+		free_species(h);
+		h = old;
+		return rc;
+	}
 	k_regrow<<<(s->nb + 7) / 8, 256, 0, s->stream>>>(old.d, h.d, s->g, s->nb, old.arr);
 	CK(cudaGetLastError());
 	CK(cudaStreamSynchronize(s->stream));
@@ -993,6 +1072,7 @@ extern "C" int
 cpic_b200_stage_field_E(cpic_b200_sim_t *s)
 {
 	if(!s) return fail(CPIC_B200_EINVAL, "null sim");
+	if(s->p.nranks > 1 && !s->comm) return fail(CPIC_B200_EINVAL, "rank %d of %d has no communicator: call cpic_b200_comm_init first", s->p.rank, s->p.nranks);
 	CK(cudaSetDevice(s->device));
 	const Geom &g = s->g;
 	int rc;
@@ -1045,14 +1125,7 @@ launch_gather_push(sim_t_ *s, int is, cudaStream_t stream)
 	SpeciesHost &h = s->sp[is];
 	if(!h.block) return 0;
 	const Geom &g = s->g;
-	/* the opt-in limit is per function and process wide: only ever raise it */
-	static size_t attr_smem[3] = { 0, 0, 0 };
-	const size_t smem = s->smem_push + (size_t) g.WPC * PIPE_STAGES * PipeArrays<MODE>::N * 32 * sizeof(double);
-	if(smem > attr_smem[MODE])
-	{
-		CK(cudaFuncSetAttribute(k_gather_push<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-		attr_smem[MODE] = smem;
-	}
+	const size_t smem = push_smem_bytes<MODE>(s);
 	const int ctas = s->nb / g.WPC;
 	/* a push reads the pending arrivals and fills the other outbox */
 	const int cur = MODE == 0 ? h.arr : h.arr ^ 1;
@@ -1067,6 +1140,7 @@ extern "C" int
 cpic_b200_stage_plasma_E(cpic_b200_sim_t *s)
 {
 	if(!s) return fail(CPIC_B200_EINVAL, "null sim");
+	if(s->p.nranks > 1 && !s->comm) return fail(CPIC_B200_EINVAL, "rank %d of %d has no communicator: call cpic_b200_comm_init first", s->p.rank, s->p.nranks);
 	CK(cudaSetDevice(s->device));
 	StageTimer t(s, T_GATHER);
 	for(int is = 0; is < s->p.nspecies; is++)
@@ -1153,6 +1227,7 @@ extern "C" int
 cpic_b200_stage_plasma_r(cpic_b200_sim_t *s)
 {
 	if(!s) return fail(CPIC_B200_EINVAL, "null sim");
+	if(s->p.nranks > 1 && !s->comm) return fail(CPIC_B200_EINVAL, "rank %d of %d has no communicator: call cpic_b200_comm_init first", s->p.rank, s->p.nranks);
 	CK(cudaSetDevice(s->device));
 	return stage_plasma_r<1>(s);
 }
@@ -1162,19 +1237,10 @@ extern "C" int
 cpic_b200_stage_field_rho(cpic_b200_sim_t *s)
 {
 	if(!s) return fail(CPIC_B200_EINVAL, "null sim");
+	if(s->p.nranks > 1 && !s->comm) return fail(CPIC_B200_EINVAL, "rank %d of %d has no communicator: call cpic_b200_comm_init first", s->p.rank, s->p.nranks);
 	CK(cudaSetDevice(s->device));
 	StageTimer t(s, T_RHO);
 	const Geom &g = s->g;
-	const int ctas = s->nb / g.WPC;
-	const int ncx = g.nbx / g.WPC;
-	bool first = true;
-	static size_t dep_attr = 0;
-	if(s->smem_dep > dep_attr)
-	{
-		CK(cudaFuncSetAttribute(k_deposit<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) s->smem_dep));
-		CK(cudaFuncSetAttribute(k_deposit<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) s->smem_dep));
-		dep_attr = s->smem_dep;
-	}
 	static_assert(DEP_MAX_SPECIES >= CPIC_B200_MAX_SPECIES, "deposit set too small");
 	DepositSet set;
 	set.n = 0;
@@ -1190,44 +1256,46 @@ cpic_b200_stage_field_rho(cpic_b200_sim_t *s)
 		d.cap = h.d.cap; d.nob = h.d.nob;
 		memcpy(d.roff, h.d.roff, sizeof(d.roff));
 		memcpy(d.rcap, h.d.rcap, sizeof(d.rcap));
-		first = false;
 	}
-	if(set.n && DEP_FUSED)
-	{
-		/* every species in one pass over the blocks */
-		k_deposit<true><<<ctas, 32 * g.WPC, s->smem_dep, s->stream>>>(set, g, s->nb, s->rho, s->hb, s->hr, s->hc);
-		int rc = check_launch(s);
-		if(rc) return rc;
-	}
-	else
-		for(int k = 0; k < set.n; k++)
-		{
-			DepositSet one;
-			one.s[0] = set.s[k];
-			one.n = 1;
-			if(k == 0) k_deposit<true><<<ctas, 32 * g.WPC, s->smem_dep, s->stream>>>(one, g, s->nb, s->rho, s->hb, s->hr, s->hc);
-			else k_deposit<false><<<ctas, 32 * g.WPC, s->smem_dep, s->stream>>>(one, g, s->nb, s->rho, s->hb, s->hr, s->hc);
-			int rc = check_launch(s);
-			if(rc) return rc;
-		}
-	if(first)
+	if(!set.n)
 	{
 		/* no particles at all: rho_reset only */
 		CK(cudaMemsetAsync(s->rho, 0, (size_t) (g.ny + 1) * g.S * sizeof(double), s->stream));
 	}
 	else
 	{
-		k_stitch<<<dim3((std::max(g.nx, g.ny) + 127) / 128, g.nby + ncx), 128, 0, s->stream>>>(s->rho, s->hb, s->hr, s->hc, g);
+		/* a persistent grid: as many CTAs as fit the device at once, blocks handed out round-robin */
+		const int ctas = std::min((s->nb + DEP_WARPS - 1) / DEP_WARPS, s->dep_ctas);
+		if(DEP_FUSED)
+		{
+			/* every species in one pass over the blocks */
+			k_deposit<true><<<ctas, 32 * DEP_WARPS, s->smem_dep, s->stream>>>(set, g, s->nb, s->dep_cols, s->tiles);
+			int rc = check_launch(s);
+			if(rc) return rc;
+		}
+		else
+			for(int k = 0; k < set.n; k++)
+			{
+				DepositSet one;
+				one.s[0] = set.s[k];
+				one.n = 1;
+				if(k == 0) k_deposit<true><<<ctas, 32 * DEP_WARPS, s->smem_dep, s->stream>>>(one, g, s->nb, s->dep_cols, s->tiles);
+				else k_deposit<false><<<ctas, 32 * DEP_WARPS, s->smem_dep, s->stream>>>(one, g, s->nb, s->dep_cols, s->tiles);
+				int rc = check_launch(s);
+				if(rc) return rc;
+			}
+		/* one rank: the ghost row goes to ourselves (comm_send_ghost_rho / comm_recv_ghost_rho, reference
+		 * src/comm_field.c:51-136) and is folded into row 0 by the same pass */
+		k_rho_assemble<<<dim3((g.nx + 127) / 128, g.ny + 1), 128, 0, s->stream>>>(s->tiles, s->rho, g, s->comm ? 0 : 1);
 		int rc = check_launch(s);
 		if(rc) return rc;
 	}
-	/* comm_send_ghost_rho / comm_recv_ghost_rho, reference src/comm_field.c:51-136 */
 	if(s->comm)
 	{
 		int rc = comm_rho_halo(s->comm, s->rho, s->stream, &s->launches);
 		if(rc) return rc;
 	}
-	else
+	else if(!set.n)
 	{
 		k_rho_fold<<<(g.nx + 127) / 128, 128, 0, s->stream>>>(s->rho, s->rho + (size_t) g.ny * g.S, g);
 		int rc = check_launch(s);

@@ -186,6 +186,10 @@ class Sim:
     def init_uniform(self, species, n, id0=0, vx=0.0, vy=0.0, seed=138):
         check(self.L.cpic_b200_init_uniform(self.h, species, n, id0, vx, vy, seed))
 
+    def init_beam(self, species, n, id0=0, drift=(0.0, 0.0), spread=(0.0, 0.0), seed=138):
+        """Device initialiser: uniform positions, u = drift + U(-spread, spread) per axis."""
+        check(self.L.cpic_b200_init_beam(self.h, species, n, id0, drift[0], drift[1], spread[0], spread[1], seed))
+
     def num_particles(self, species):
         return self.L.cpic_b200_num_particles(self.h, species)
 

@@ -51,6 +51,15 @@ attach(sim_t *sim)
 	i64 is, ic;
 
 	if(D.gpu) return;
+	if(sim->nprocs > 1)
+	{
+		/* one process = one GPU slab needs the NCCL bootstrap (cpic_b200_comm_id on rank 0, the id
+		 * broadcast with MPI_Bcast, cpic_b200_comm_init on every rank) before the first stage, and a
+		 * host id -> slot map that follows the particles between ranks: this binding does neither */
+		fprintf(stderr, "cpic_b200 drop-in: %d MPI processes: this binding drives one rank on one GPU; "
+				"several GPUs run through cpic_b200_sim_from_conf + cpic_b200_comm_init (INTEGRATION.md)\n", sim->nprocs);
+		abort();
+	}
 	memset(&p, 0, sizeof(p));
 	p.nx = sim->ntpoints[X];
 	p.ny = sim->ntpoints[Y];

@@ -120,6 +120,10 @@ int64_t cpic_b200_get_particles(cpic_b200_sim_t *sim, int species, int64_t cap,
  * counter-based generator, not glibc rand(). n is this rank's share. */
 int cpic_b200_init_uniform(cpic_b200_sim_t *sim, int species, int64_t n, int64_t id0,
 		double vx, double vy, uint64_t seed);
+/* Same with a drift: u = (dux, duy) + U(-v, v) per axis -- a warm beam (the reference's
+ * "position delta" initialiser gives every particle the drift velocity, src/particle.c:152-153) */
+int cpic_b200_init_beam(cpic_b200_sim_t *sim, int species, int64_t n, int64_t id0,
+		double dux, double duy, double vx, double vy, uint64_t seed);
 
 /* ---- the four stages, in sim_step order (src/sim.c:503,517,525,536) ---- */
 int cpic_b200_stage_field_E(cpic_b200_sim_t *sim);     /* src/field.c:450-501 */

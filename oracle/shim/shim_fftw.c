@@ -12,6 +12,11 @@
  * other lengths fall back to a direct O(n^2) DFT (small test grids only).
  * No value is ever scaled into the denormal range (the reference traps FE_UNDERFLOW,
  * src/sim.c:102-106).
+ *
+ * -DSHIM_MP (cpic_ref_mp, with shim_mpi_mp.c): the same transforms over P forked ranks, each
+ * owning n0/P rows as FFTW-MPI's slab decomposition does (fftw_mpi_local_size_2d): row
+ * transforms of the local rows into a work array in the shared mapping, barrier, column
+ * transforms of a 1/P share of the columns, barrier, local rows back out.
  */
 #define _GNU_SOURCE
 #include "fftw3.h"
@@ -32,9 +37,18 @@ typedef struct fft1d {
 	cplx *tmp;
 } fft1d_t;
 
+#ifdef SHIM_MP
+int shim_mp_rank(void);
+int shim_mp_size(void);
+void shim_mp_barrier(void);
+void *shim_mp_shared_alloc(size_t bytes);
+#endif
+
 struct shim_fftw_plan {
 	int kind;         /* 0 = r2c, 1 = c2r */
 	ptrdiff_t n0, n1;
+	ptrdiff_t l0, y0; /* local rows and first local row (n0, 0 on one rank) */
+	cplx *work;       /* n0 x (n1/2+1): the whole spectrum (shared between the ranks with SHIM_MP) */
 	double *real;
 	cplx *cpx;
 	fft1d_t f0, f1;
@@ -142,13 +156,15 @@ static void
 exec_r2c(struct shim_fftw_plan *p)
 {
 	ptrdiff_t n0 = p->n0, n1 = p->n1, nc = n1 / 2 + 1, ld = 2 * nc;
+	ptrdiff_t l0 = p->l0;
 	ptrdiff_t y, x, k;
+	cplx *W = p->work + p->y0 * nc;        /* this rank's rows of the whole spectrum */
 
 	/* Pass 1: rows. Two real rows share one complex transform. */
-	for(y = 0; y + 1 < n0; y += 2)
+	for(y = 0; y + 1 < l0; y += 2)
 	{
 		double *a = p->real + y * ld, *b = a + ld;
-		cplx *oa = p->cpx + y * nc, *ob = oa + nc;
+		cplx *oa = W + y * nc, *ob = oa + nc;
 		for(x = 0; x < n1; x++) p->row[x] = a[x] + b[x] * I;
 		fft1d_exec(&p->f1, p->row, -1);
 		for(k = 0; k < nc; k++)
@@ -160,43 +176,69 @@ exec_r2c(struct shim_fftw_plan *p)
 			ob[k] = 0.5 * (cimag(d) - creal(d) * I);
 		}
 	}
-	if(y < n0)
+	if(y < l0)
 	{
 		double *a = p->real + y * ld;
-		cplx *oa = p->cpx + y * nc;
+		cplx *oa = W + y * nc;
 		for(x = 0; x < n1; x++) p->row[x] = a[x];
 		fft1d_exec(&p->f1, p->row, -1);
 		for(k = 0; k < nc; k++) oa[k] = p->row[k];
 	}
 
-	/* Pass 2: columns */
-	for(k = 0; k < nc; k++)
+	/* Pass 2: columns (a share of them per rank) */
+	ptrdiff_t k0 = 0, k1 = nc;
+#ifdef SHIM_MP
+	k0 = nc * shim_mp_rank() / shim_mp_size();
+	k1 = nc * (shim_mp_rank() + 1) / shim_mp_size();
+	shim_mp_barrier();
+#endif
+	for(k = k0; k < k1; k++)
 	{
-		for(y = 0; y < n0; y++) p->col[y] = p->cpx[y * nc + k];
+		for(y = 0; y < n0; y++) p->col[y] = p->work[y * nc + k];
 		fft1d_exec(&p->f0, p->col, -1);
-		for(y = 0; y < n0; y++) p->cpx[y * nc + k] = p->col[y];
+		for(y = 0; y < n0; y++) p->work[y * nc + k] = p->col[y];
 	}
+#ifdef SHIM_MP
+	shim_mp_barrier();
+#endif
+	if(p->cpx != W) memcpy(p->cpx, W, (size_t) (l0 * nc) * sizeof(cplx));
+#ifdef SHIM_MP
+	shim_mp_barrier();      /* nobody refills the work array before everybody has copied */
+#endif
 }
 
 static void
 exec_c2r(struct shim_fftw_plan *p)
 {
 	ptrdiff_t n0 = p->n0, n1 = p->n1, nc = n1 / 2 + 1, ld = 2 * nc;
+	ptrdiff_t l0 = p->l0;
 	ptrdiff_t y, x, k;
+	cplx *W = p->work + p->y0 * nc;
 
-	/* Pass 1: columns, backward */
-	for(k = 0; k < nc; k++)
+	if(p->cpx != W) memcpy(W, p->cpx, (size_t) (l0 * nc) * sizeof(cplx));
+
+	/* Pass 1: columns, backward (a share of them per rank) */
+	ptrdiff_t k0 = 0, k1 = nc;
+#ifdef SHIM_MP
+	k0 = nc * shim_mp_rank() / shim_mp_size();
+	k1 = nc * (shim_mp_rank() + 1) / shim_mp_size();
+	shim_mp_barrier();
+#endif
+	for(k = k0; k < k1; k++)
 	{
-		for(y = 0; y < n0; y++) p->col[y] = p->cpx[y * nc + k];
+		for(y = 0; y < n0; y++) p->col[y] = p->work[y * nc + k];
 		fft1d_exec(&p->f0, p->col, +1);
-		for(y = 0; y < n0; y++) p->cpx[y * nc + k] = p->col[y];
+		for(y = 0; y < n0; y++) p->work[y * nc + k] = p->col[y];
 	}
+#ifdef SHIM_MP
+	shim_mp_barrier();
+#endif
 
 	/* Pass 2: rows, Hermitian-extended, two at a time */
-	for(y = 0; y < n0; y += 2)
+	for(y = 0; y < l0; y += 2)
 	{
-		int pair = (y + 1 < n0);
-		cplx *ia = p->cpx + y * nc, *ib = ia + nc;
+		int pair = (y + 1 < l0);
+		cplx *ia = W + y * nc, *ib = ia + nc;
 		double *a = p->real + y * ld, *b = a + ld;
 
 		for(k = 0; k < nc; k++)
@@ -223,6 +265,9 @@ exec_c2r(struct shim_fftw_plan *p)
 			if(pair) b[x] = cimag(p->row[x]);
 		}
 	}
+#ifdef SHIM_MP
+	shim_mp_barrier();
+#endif
 }
 
 void
@@ -242,6 +287,16 @@ plan_new(int kind, ptrdiff_t n0, ptrdiff_t n1, double *real, cplx *cpx)
 	p->n1 = n1;
 	p->real = real;
 	p->cpx = cpx;
+#ifdef SHIM_MP
+	p->l0 = n0 / shim_mp_size();
+	p->y0 = p->l0 * shim_mp_rank();
+	p->work = shim_mp_shared_alloc((size_t) (n0 * (n1 / 2 + 1)) * sizeof(cplx));
+#else
+	/* one rank: the caller's complex array is the whole spectrum; transformed in place */
+	p->l0 = n0;
+	p->y0 = 0;
+	p->work = cpx;
+#endif
 	fft1d_init(&p->f0, n0);
 	fft1d_init(&p->f1, n1);
 	p->col = malloc((size_t) n0 * sizeof(cplx));
@@ -282,9 +337,15 @@ fftw_mpi_local_size_2d(ptrdiff_t n0, ptrdiff_t n1, MPI_Comm comm,
 		ptrdiff_t *local_n0, ptrdiff_t *local_0_start)
 {
 	(void) comm;
+#ifdef SHIM_MP
+	*local_n0 = n0 / shim_mp_size();
+	*local_0_start = *local_n0 * shim_mp_rank();
+	return *local_n0 * n1;
+#else
 	*local_n0 = n0;
 	*local_0_start = 0;
 	return n0 * n1;
+#endif
 }
 
 void fftw_mpi_init(void) {}

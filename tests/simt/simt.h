@@ -152,6 +152,15 @@ template <typename F> static inline cudaError_t cudaFuncSetAttribute(F *, cudaFu
 	return bytes <= 227 * 1024 ? cudaSuccess : cudaErrorInvalidValue;
 }
 
+/* a small "device": 4 SMs with 2 resident CTAs each, so that persistent grids loop over their work */
+enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount = 16 };
+static inline cudaError_t cudaDeviceGetAttribute(int *v, cudaDeviceAttr, int) { *v = 4; return cudaSuccess; }
+template <typename F> static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, F *, int, size_t)
+{
+	*n = 2;
+	return cudaSuccess;
+}
+
 /* ---- driver API: tensor maps ---- */
 typedef int CUresult;
 enum { CUDA_SUCCESS = 0, CUDA_ERROR_INVALID_VALUE = 1 };

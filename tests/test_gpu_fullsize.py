@@ -22,7 +22,7 @@ def test_config_A_full_size():
     o.pre_step()
     g.pre_step()
     assert_close(field_errors(g, o), what="config A after sim_init")
-    for it in range(2):
+    for it in range(10):      # BASELINE.json north_star: the first 10 steps
         g.step()
         o.step()
         g.sync()
@@ -53,3 +53,23 @@ def test_config_A_full_size():
     # 5. B only rotates and the field energy is tiny in this weakly coupled plasma: kinetic energy drifts little
     ke1, _ = g.energy()
     assert abs(ke1 - ke0) / ke0 < 1e-4
+
+
+def test_config_B_cyclotron_2048_first_steps():
+    """BASELINE.json configs[2]: conf/cyclotron-2048.conf (uniform B, 2048^2 grid, 1e8 particles) from the
+    reference's own initial conditions: sim_init and three iterations against the oracle."""
+    conf = conf_path("cyclotron-2048.conf")
+    params, run = load_conf(conf)
+    parts = init_particles(conf)
+    assert sum(len(p["id"]) for p in parts) == 100_000_000
+    o = oracle_from(params, parts)
+    g = gpu_from(params, parts)
+    o.pre_step()
+    g.pre_step()
+    assert_close(field_errors(g, o), what="config B after sim_init")
+    for it in range(3):
+        g.step()
+        o.step()
+        g.sync()
+        assert_close(field_errors(g, o), what=f"config B fields, iteration {it}")
+        assert_close(particle_errors(g, o, params), what=f"config B particles, iteration {it}")

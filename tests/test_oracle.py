@@ -195,3 +195,62 @@ def test_two_stream_growth_rate():
     slope = np.polyfit(t[sel], np.log(ex2[sel]), 1)[0]
     gamma = np.sqrt(np.sqrt(5.0) - 2.0)
     assert abs(slope / 2.0 - gamma) / gamma < 0.15, (slope / 2.0, gamma)
+
+
+# ---- the multi-process shims behind the CPU baseline (oracle/shim/shim_mpi_mp.c, shim_fftw.c -DSHIM_MP)
+
+def _mp_run(conf, nprocs, steps, tmp):
+    """oracle/_ref/ref_mp_check: the unmodified reference (accumulate-correct deposit) over `nprocs`
+    forked ranks; returns the assembled slabs and the particles sorted by id."""
+    import subprocess
+    d = os.path.join(tmp, f"p{nprocs}")
+    os.makedirs(d, exist_ok=True)
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_mp_check")
+    r = subprocess.run([exe, conf, str(steps), d], env=dict(os.environ, CPIC_SHIM_NPROCS=str(nprocs)),
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-2000:]
+    fields = {k: [] for k in ("rho", "phi", "Ex", "Ey")}
+    parts = None
+    for rank in range(nprocs):
+        b = open(os.path.join(d, f"rank{rank}.bin"), "rb").read()
+        nx, ny, ns = (int(v) for v in np.frombuffer(b, np.int64, 3, 0))
+        off = 24
+        for k in fields:
+            rows = int(np.frombuffer(b, np.int64, 1, off)[0])
+            off += 8
+            fields[k].append(np.frombuffer(b, np.float64, rows * nx, off).reshape(rows, nx)[:ny])
+            off += 8 * rows * nx
+        if parts is None:
+            parts = [{k: [] for k in ("id", "x", "y", "ux", "uy")} for _ in range(ns)]
+        for s in range(ns):
+            n = int(np.frombuffer(b, np.int64, 1, off)[0])
+            off += 8
+            parts[s]["id"].append(np.frombuffer(b, np.int64, n, off))
+            off += 8 * n
+            for k in ("x", "y", "ux", "uy"):
+                parts[s][k].append(np.frombuffer(b, np.float64, n, off))
+                off += 8 * n
+    out = []
+    for s in parts:
+        q = {k: np.concatenate(v) for k, v in s.items()}
+        o = np.argsort(q["id"], kind="stable")
+        out.append({k: v[o] for k, v in q.items()})
+    return {k: np.vstack(v) for k, v in fields.items()}, out
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ref_mp_check")),
+                    reason="oracle/_ref/ref_mp_check not built (needs /root/reference)")
+@pytest.mark.parametrize("conf,ranks", [("two-streams.conf", (2, 4)), ("2d-2species-delta.conf", (2,))])
+def test_reference_over_forked_ranks_equals_single_rank(conf, ranks, tmp_path):
+    """The CPU baseline runs the unmodified reference with one forked rank per core over socket and
+    shared-memory stand-ins for MPI and FFTW-MPI: 10 steps on P ranks must reproduce the single-rank
+    run (position-delta initial conditions do not depend on the number of ranks)."""
+    F1, P1 = _mp_run(conf_path(conf), 1, 10, str(tmp_path))
+    for nprocs in ranks:
+        F, P = _mp_run(conf_path(conf), nprocs, 10, str(tmp_path))
+        for k in F1:
+            assert relerr(F[k], F1[k]) <= TOL, (conf, nprocs, k)
+        for a, b in zip(P, P1):
+            assert np.array_equal(a["id"], b["id"])
+            for k, scale in (("x", 1.0), ("y", 1.0), ("ux", np.abs(b["ux"]).max()), ("uy", max(np.abs(b["uy"]).max(), 1e-300))):
+                assert np.abs(a[k] - b[k]).max() / scale <= 1e-11, (conf, nprocs, k)
