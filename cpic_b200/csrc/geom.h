@@ -40,6 +40,7 @@
 #define ERRBIT_REGION 16      /* an exchange region overflowed */
 #define ERRBIT_FARLIST 32     /* more far movers in one step than the list holds */
 #define ERRBIT_ABSORB 64      /* a block could not take its arrivals */
+#define ERRBIT_PEER 128       /* a neighbour rank did not arrive at an exchange */
 
 /* One rank's slab and its decomposition into particle blocks of BX x BY cells */
 struct Geom {
@@ -68,6 +69,17 @@ struct Geom {
  * addressable. Rows are always formed from the GLOBAL coordinate (floor(y * idy)) and then
  * made slab-relative as integers: every kernel and the host binning agree on the cell of a
  * particle whatever the rank, and the arithmetic is that of the single-rank reference. */
+/* clamp into [0, hi]: one min and one max instruction on the device */
+HD int
+clamp0(int c, int hi)
+{
+#ifdef __CUDA_ARCH__
+	return min(max(c, 0), hi);
+#else
+	return c < 0 ? 0 : (c > hi ? hi : c);
+#endif
+}
+
 HD int
 cell_ix(const Geom &g, double x)
 {
@@ -76,7 +88,7 @@ cell_ix(const Geom &g, double x)
 #else
 	int c = (int) floor(x * g.idx);
 #endif
-	return c < 0 ? 0 : (c > g.nx - 1 ? g.nx - 1 : c);
+	return clamp0(c, g.nx - 1);
 }
 
 /* Global row of a position */
@@ -88,15 +100,14 @@ global_row(const Geom &g, double y)
 #else
 	int c = (int) floor(y * g.idy);
 #endif
-	return c < 0 ? 0 : (c > g.ny_glob - 1 ? g.ny_glob - 1 : c);
+	return clamp0(c, g.ny_glob - 1);
 }
 
 /* Row inside this rank's slab */
 HD int
 cell_iy(const Geom &g, double y)
 {
-	int c = global_row(g, y) - g.row0;
-	return c < 0 ? 0 : (c > g.ny - 1 ? g.ny - 1 : c);
+	return clamp0(global_row(g, y) - g.row0, g.ny - 1);
 }
 
 /* Bilinear (CIC) weights, restating reference src/interpolate.c:77-100 (weights),

@@ -93,6 +93,11 @@ struct SpeciesDev {
 	long long *id;
 	int *count;              /* particles in the block's own segment */
 	Outbox ob[2];
+	/* The outboxes of the neighbour ranks, mapped over NVLink (CUDA IPC): pob[0] the north
+	 * rank's, pob[1] the south rank's, both buffers. With them a leaver that crosses a slab face is
+	 * written straight into the GHOST OUTBOX ROW of its new rank (rec == NULL: no peer mapping, the
+	 * face regions travel by NCCL, comm.cu) */
+	Outbox pob[2][2];
 	int cap;                 /* slots per block segment */
 	unsigned astride;        /* doubles between the segment arrays x y ux uy uz id (one allocation) */
 	int ocs, occ;            /* slots per side / corner region */
@@ -328,6 +333,47 @@ k_rho_fold(double *__restrict__ rho, const double *__restrict__ recv, Geom g)
 	int x = blockIdx.x * blockDim.x + threadIdx.x;
 	if(x >= g.nx) return;
 	rho[x] += recv[x];
+}
+
+/* ------------------------------------------------ peer synchronisation (several ranks) */
+
+/* Ranks that write into each other's memory over NVLink meet through flag words: after the
+ * kernels that produced the data, k_peer_signal stores the sequence number of the exchange into
+ * flag `slot` of every listed peer (system-scope fence first: the data is visible before the
+ * flag); k_peer_wait spins until its own flags, written by those peers, have reached the number.
+ * A peer that never arrives raises ERRBIT_PEER instead of hanging the device. */
+#define PEER_MAX 16
+struct PeerJob {
+	int *flag[PEER_MAX];     /* signal: the peers' flag arrays; wait: n times the own array */
+	int slot[PEER_MAX];      /* the word of each */
+	int n;
+	int value;
+};
+
+static __global__ void
+k_peer_signal(const __grid_constant__ PeerJob job)
+{
+	__threadfence_system();
+	if((int) threadIdx.x < job.n)
+		*(volatile int *) (job.flag[threadIdx.x] + job.slot[threadIdx.x]) = job.value;
+}
+
+static __global__ void
+k_peer_wait(const __grid_constant__ PeerJob job, int *__restrict__ errflag)
+{
+	if((int) threadIdx.x >= job.n) return;
+	const volatile int *f = job.flag[threadIdx.x] + job.slot[threadIdx.x];
+#ifdef CPIC_B200_SIMT_CHECK
+	if(*f - job.value < 0) atomicOr(errflag, ERRBIT_PEER);       /* one process at a time: nobody to wait for */
+#else
+	const long long t0 = clock64();
+	while(*f - job.value < 0)
+	{
+		if(clock64() - t0 > 20000000000LL) { atomicOr(errflag, ERRBIT_PEER); break; }      /* ~10 s */
+		__nanosleep(200);
+	}
+	__threadfence_system();
+#endif
 }
 
 /* ---------------------------------------------------------- particle kernels */
@@ -763,12 +809,19 @@ k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 				}
 				else
 				{
-					const size_t o = region_slot(sp, dest, b, pos);
-					double2 *r = (double2 *) (out.rec + o * OREC);
+					/* a leaver that crosses a slab face goes straight to the ghost outbox row of the
+					 * neighbour rank (peer memory): what row 0 sends north is the north rank's south ghost
+					 * row, what the last row sends south the south rank's north ghost row */
+					const Outbox *po = &out;
+					int rb = b;
+					if(dest < 3 && by == 0 && sp.pob[0][cur].rec) { po = &sp.pob[0][cur]; rb = nb + g.nbx + bx; }
+					else if(dest > 5 && by == g.nby - 1 && sp.pob[1][cur].rec) { po = &sp.pob[1][cur]; rb = nb + bx; }
+					const size_t o = region_slot(sp, dest, rb, pos);
+					double2 *r = (double2 *) (po->rec + o * OREC);
 					r[0] = make_double2(x, y);
 					r[1] = make_double2(ux, uy);
 					r[2] = make_double2(uz, __longlong_as_double(pid));
-					if(out.recE) *(double2 *) (out.recE + o * 2) = make_double2(Ex, Ey);
+					if(po->recE) *(double2 *) (po->recE + o * 2) = make_double2(Ex, Ey);
 				}
 			}
 			__syncwarp();
@@ -784,7 +837,19 @@ k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 		{
 			const int v = ocnt[lane];
 			const int rc = sp.rcap[lane];
-			out.count[(size_t) lane * sp.nob + b] = v < rc ? v : rc;
+			int n = v < rc ? v : rc;
+			/* the counters of the regions that were written into a neighbour rank's ghost row */
+			if(lane < 3 && by == 0 && sp.pob[0][cur].rec)
+			{
+				sp.pob[0][cur].count[(size_t) lane * sp.nob + nb + g.nbx + bx] = n;
+				n = 0;
+			}
+			else if(lane > 5 && by == g.nby - 1 && sp.pob[1][cur].rec)
+			{
+				sp.pob[1][cur].count[(size_t) lane * sp.nob + nb + bx] = n;
+				n = 0;
+			}
+			out.count[(size_t) lane * sp.nob + b] = n;
 		}
 		if(bad)
 		{
@@ -1108,11 +1173,14 @@ dep_add(double *t, const DepContribution &c, int ncol, int rowstep)
 	q1[ncol] = ADD(v11, c.a11);
 }
 
-template <bool FIRST>
+/* NCOL > 0: the number of columns is a compile-time constant (the shipped 16: two groups of a
+ * half-warp each); NCOL == 0: `ncol_rt` columns, any power of two up to 16 (large particle blocks) */
+template <bool FIRST, int NCOL>
 __global__ void __launch_bounds__(32 * DEP_WARPS)
-k_deposit(const __grid_constant__ DepositSet set, Geom g, int nb, int ncol, double *__restrict__ tiles)
+k_deposit(const __grid_constant__ DepositSet set, Geom g, int nb, int ncol_rt, double *__restrict__ tiles)
 {
 	extern __shared__ __align__(128) unsigned char smem[];
+	const int ncol = NCOL > 0 ? NCOL : ncol_rt;
 	const int NW = g.BX + 1;                     /* nodes per tile row */
 	const int NN = NW * (g.BY + 1);              /* nodes per block tile */
 	const int wsz = NN * ncol;                   /* accumulators per warp: [node][column] */
@@ -1122,6 +1190,12 @@ k_deposit(const __grid_constant__ DepositSet set, Geom g, int nb, int ncol, doub
 	const int rowstep = NW * ncol;
 	__shared__ int scratch_[DEP_WARPS][20];
 	int *scratch = scratch_[warp];
+
+	/* the lane's turn: groups one after the other, a warp barrier in between */
+#define DEP_TURN(BODY) do { \
+	if(NCOL == 16) { \
+		if(grp == 0) { BODY } __syncwarp(); if(grp == 1) { BODY } __syncwarp(); \
+	} else for(int p_ = 0; p_ < ngrp; p_++) { if(grp == p_) { BODY } __syncwarp(); } } while(0)
 
 	for(int b = blockIdx.x * DEP_WARPS + warp; b < nb; b += gridDim.x * DEP_WARPS)
 	{
@@ -1140,45 +1214,42 @@ k_deposit(const __grid_constant__ DepositSet set, Geom g, int nb, int ncol, doub
 #if SEG_AOSOA
 #error "k_deposit walks plain segments"
 #endif
-			/* own segment: two particles per lane and turn, the next two already on their way */
+			/* own segment: two particles per lane and turn, the next four already on their way */
 			int k = lane;
-			double xa = 0, ya = 0, xb = 0, yb = 0;
+			double xa = 0, ya = 0, xb = 0, yb = 0, xc = 0, yc = 0, xd = 0, yd = 0;
 			if(k < cnt) { xa = sx[k]; ya = sy[k]; }
 			if(k + 32 < cnt) { xb = sx[k + 32]; yb = sy[k + 32]; }
+			if(k + 64 < cnt) { xc = sx[k + 64]; yc = sy[k + 64]; }
+			if(k + 96 < cnt) { xd = sx[k + 96]; yd = sy[k + 96]; }
 			/* the arrival counters travel while the segment is walked */
 			__syncwarp();
 			const Arrivals A = find_arrivals(sp.acount, sp.nob, g, nb, b, lane, scratch);
 			for(; k - lane < cnt; k += 64)
 			{
-				double nxa = 0, nya = 0, nxb = 0, nyb = 0;
-				if(k + 64 < cnt) { nxa = sx[k + 64]; nya = sy[k + 64]; }
-				if(k + 96 < cnt) { nxb = sx[k + 96]; nyb = sy[k + 96]; }
+				double nx_ = 0, ny_ = 0, mx_ = 0, my_ = 0;
+				if(k + 128 < cnt) { nx_ = sx[k + 128]; ny_ = sy[k + 128]; }
+				if(k + 160 < cnt) { mx_ = sx[k + 160]; my_ = sy[k + 160]; }
 				const DepContribution ca = dep_contribution(g, xa, ya, vq, k < cnt, cx0, cy0, NW, ncol, col);
 				const DepContribution cb = dep_contribution(g, xb, yb, vq, k + 32 < cnt, cx0, cy0, NW, ncol, col);
-				for(int p = 0; p < ngrp; p++)
-				{
-					if(grp == p) { dep_add(t, ca, ncol, rowstep); dep_add(t, cb, ncol, rowstep); }
-					__syncwarp();
-				}
-				xa = nxa; ya = nya; xb = nxb; yb = nyb;
+				DEP_TURN(dep_add(t, ca, ncol, rowstep); dep_add(t, cb, ncol, rowstep););
+				xa = xc; ya = yc; xb = xd; yb = yd;
+				xc = nx_; yc = ny_; xd = mx_; yd = my_;
 			}
 			/* arrivals: (x, y) are the first 16 bytes of a 48-byte record */
 			int f = lane;
-			double2 v = make_double2(0.0, 0.0);
+			double2 v = make_double2(0.0, 0.0), v2 = make_double2(0.0, 0.0);
 			if(f < A.total) v = *(const double2 *) (sp.arec + (size_t) arrival_slot(A, sp.roff, sp.rcap, f) * OREC);
+			if(f + 32 < A.total) v2 = *(const double2 *) (sp.arec + (size_t) arrival_slot(A, sp.roff, sp.rcap, f + 32) * OREC);
 			for(; f - lane < A.total; f += 32)
 			{
 				double2 nv = make_double2(0.0, 0.0);
-				if(f + 32 < A.total) nv = *(const double2 *) (sp.arec + (size_t) arrival_slot(A, sp.roff, sp.rcap, f + 32) * OREC);
+				if(f + 64 < A.total) nv = *(const double2 *) (sp.arec + (size_t) arrival_slot(A, sp.roff, sp.rcap, f + 64) * OREC);
 				const DepContribution ca = dep_contribution(g, v.x, v.y, vq, f < A.total, cx0, cy0, NW, ncol, col);
-				for(int p = 0; p < ngrp; p++)
-				{
-					if(grp == p) dep_add(t, ca, ncol, rowstep);
-					__syncwarp();
-				}
-				v = nv;
+				DEP_TURN(dep_add(t, ca, ncol, rowstep););
+				v = v2; v2 = nv;
 			}
 		}
+#undef DEP_TURN
 
 		/* the columns of every node, in a fixed order that starts at a different column for
 		 * neighbouring nodes (conflict-free reads) */

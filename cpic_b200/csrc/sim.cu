@@ -101,6 +101,7 @@ struct cpic_b200_sim {
 	SpeciesHost sp[CPIC_B200_MAX_SPECIES];
 
 	Comm *comm;              /* NULL on one rank */
+	bool p2p_stale;          /* the peers do not know this rank's current species storage (comm.h: peer memory) */
 
 	bool timing;
 	cudaEvent_t ev[2];
@@ -328,11 +329,13 @@ cpic_b200_create(const cpic_b200_params_t *pp, cpic_b200_sim_t **out)
 	s->smem_dep = (size_t) DEP_WARPS * (g.BX + 1) * (g.BY + 1) * s->dep_cols * sizeof(double);
 	/* the opt-in shared-memory limits are per function AND per device: set them for this
 	 * simulation's device, whatever another simulation of the process did on another one */
-	CKD(cudaFuncSetAttribute(k_deposit<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) s->smem_dep));
-	CKD(cudaFuncSetAttribute(k_deposit<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) s->smem_dep));
+	CKD((cudaFuncSetAttribute(k_deposit<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) s->smem_dep)));
+	CKD((cudaFuncSetAttribute(k_deposit<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) s->smem_dep)));
+	CKD((cudaFuncSetAttribute(k_deposit<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) s->smem_dep)));
+	CKD((cudaFuncSetAttribute(k_deposit<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) s->smem_dep)));
 	{
 		int per_sm = 0, sms = 0;
-		CKD(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_deposit<true>, 32 * DEP_WARPS, s->smem_dep));
+		CKD((cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_deposit<true, 16>, 32 * DEP_WARPS, s->smem_dep)));
 		CKD(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
 		s->dep_ctas = std::max(1, per_sm) * std::max(1, sms);
 	}
@@ -410,6 +413,7 @@ in_slab_rows(const Geom &g, double y)
 
 static int ensure_particle_E(sim_t_ *s, int is);
 static int image_staging(sim_t_ *s, size_t doubles);
+static int p2p_attach(sim_t_ *s);
 
 static int alloc_species_storage(sim_t_ *s, int is, int cap);
 
@@ -437,6 +441,7 @@ static int
 alloc_species_storage(sim_t_ *s, int is, int cap)
 {
 	SpeciesHost &h = s->sp[is];
+	s->p2p_stale = true;
 	const size_t nslot = (size_t) s->nb * cap;
 	const size_t arr = align256(nslot * sizeof(double));
 	const size_t cnt = align256((size_t) s->nob * sizeof(int));
@@ -512,6 +517,7 @@ ensure_particle_E(sim_t_ *s, int is)
 {
 	SpeciesHost &h = s->sp[is];
 	if(h.d.pEx || !h.block) return 0;
+	s->p2p_stale = true;
 	const size_t arr = align256((size_t) s->nb * h.d.cap * sizeof(double));
 	/* (E_x, E_y) per outbox slot, next to the records */
 	const size_t oarr = align256(((size_t) h.d.roff[8] + (size_t) s->nob * h.d.rcap[8]) * 2 * sizeof(double));
@@ -861,12 +867,26 @@ check_capacity(sim_t_ *s)
 		for(int is = 0; is < s->p.nspecies; is++) { want[is] = s->h_err[1 + is]; any = any || want[is] > 0; }
 	}
 	if(!any) return 0;
+	if(s->comm && comm_p2p(s->comm))
+	{
+		/* peer memory: every rank closes its mappings of the outboxes that are about to be replaced,
+		 * and only when all have (one more reduction as a barrier) are they freed */
+		for(int is = 0; is < s->p.nspecies; is++)
+		{
+			if(want[is] <= 0 || !s->sp[is].block || want[is] <= s->sp[is].d.cap) continue;
+			if(comm_p2p_unmap(s->comm, comm_export_species(is, 0)) || comm_p2p_unmap(s->comm, comm_export_species(is, 1)))
+				return CPIC_B200_ECUDA;
+		}
+		if(comm_allreduce_max(s->comm, s->errflag + 1, 1, s->stream)) return CPIC_B200_ECUDA;
+		CK(cudaStreamSynchronize(s->stream));
+	}
 	for(int is = 0; is < s->p.nspecies; is++)
 	{
 		if(want[is] <= 0 || !s->sp[is].block || want[is] <= s->sp[is].d.cap) continue;
 		int rc = regrow(s, is, want[is]);
 		if(rc) return rc;
 	}
+	if(s->comm && s->p2p_stale) return p2p_attach(s);
 	return 0;
 }
 
@@ -1045,7 +1065,7 @@ static int
 solve(sim_t_ *s)
 {
 	const Geom &g = s->g;
-	if(s->comm) return comm_solve(s->comm, s->rho, s->phi_raw, s->stream, &s->launches);
+	if(s->comm) return comm_solve(s->comm, s->rho, s->phi_raw, s->stream, s->errflag, &s->launches);
 	const size_t n = (size_t) g.ny * (g.nx / 2 + 1);
 	CKFFT(cufftExecD2Z(s->plan_fwd, s->rho, s->gk));
 	int blocks = (int) std::min<size_t>((n + 255) / 256, 148 * 16);
@@ -1094,7 +1114,7 @@ cpic_b200_stage_field_E(cpic_b200_sim_t *s)
 	}
 	k_phi_finish<<<grid, 128, 0, s->stream>>>(s->phi_raw, s->phi, g, N, 0);
 	if((rc = check_launch(s))) return rc;
-	if((rc = comm_phi_halo(s->comm, s->phi, s->stream))) return rc;
+	if((rc = comm_phi_halo(s->comm, s->phi, s->stream, s->errflag, &s->launches))) return rc;
 	dim3 gridE((g.SE + 127) / 128, g.ny + 1);
 	k_field_E<<<gridE, 128, 0, s->stream>>>(s->phi, s->Ex, s->Ey, g);
 	return check_launch(s);
@@ -1196,22 +1216,22 @@ template <int MODE>
 static int
 stage_plasma_r(sim_t_ *s)
 {
+	if(MODE == 1)
+		for(int is = 0; is < s->p.nspecies; is++) { int rc = ensure_particle_E(s, is); if(rc) return rc; }
+	/* several ranks over peer memory: the neighbours must know where this rank's outboxes are */
+	if(s->comm && s->p2p_stale) { int rc = p2p_attach(s); if(rc) return rc; }
 	{
 		StageTimer t(s, T_PUSH);
 		/* species are independent until the exchange: odd ones go to the second stream */
 		const bool fork = s->overlap_species && s->p.nspecies > 1;
 		if(fork)
 		{
-			for(int is = 0; is < s->p.nspecies; is++)
-				if(MODE == 1) { int rc = ensure_particle_E(s, is); if(rc) return rc; }
 			CK(cudaEventRecord(s->ev_fork, s->stream));
 			CK(cudaStreamWaitEvent(s->stream2, s->ev_fork, 0));
 		}
 		for(int is = 0; is < s->p.nspecies; is++)
 		{
-			int rc = 0;
-			if(MODE == 1 && !fork) rc = ensure_particle_E(s, is);
-			if(!rc) rc = launch_gather_push<MODE>(s, is, (fork && (is & 1)) ? s->stream2 : s->stream);
+			int rc = launch_gather_push<MODE>(s, is, (fork && (is & 1)) ? s->stream2 : s->stream);
 			if(rc) return rc;
 		}
 		if(fork)
@@ -1269,7 +1289,8 @@ cpic_b200_stage_field_rho(cpic_b200_sim_t *s)
 		if(DEP_FUSED)
 		{
 			/* every species in one pass over the blocks */
-			k_deposit<true><<<ctas, 32 * DEP_WARPS, s->smem_dep, s->stream>>>(set, g, s->nb, s->dep_cols, s->tiles);
+			if(s->dep_cols == 16) k_deposit<true, 16><<<ctas, 32 * DEP_WARPS, s->smem_dep, s->stream>>>(set, g, s->nb, 16, s->tiles);
+			else k_deposit<true, 0><<<ctas, 32 * DEP_WARPS, s->smem_dep, s->stream>>>(set, g, s->nb, s->dep_cols, s->tiles);
 			int rc = check_launch(s);
 			if(rc) return rc;
 		}
@@ -1279,8 +1300,8 @@ cpic_b200_stage_field_rho(cpic_b200_sim_t *s)
 				DepositSet one;
 				one.s[0] = set.s[k];
 				one.n = 1;
-				if(k == 0) k_deposit<true><<<ctas, 32 * DEP_WARPS, s->smem_dep, s->stream>>>(one, g, s->nb, s->dep_cols, s->tiles);
-				else k_deposit<false><<<ctas, 32 * DEP_WARPS, s->smem_dep, s->stream>>>(one, g, s->nb, s->dep_cols, s->tiles);
+				if(k == 0) k_deposit<true, 0><<<ctas, 32 * DEP_WARPS, s->smem_dep, s->stream>>>(one, g, s->nb, s->dep_cols, s->tiles);
+				else k_deposit<false, 0><<<ctas, 32 * DEP_WARPS, s->smem_dep, s->stream>>>(one, g, s->nb, s->dep_cols, s->tiles);
 				int rc = check_launch(s);
 				if(rc) return rc;
 			}
@@ -1292,7 +1313,7 @@ cpic_b200_stage_field_rho(cpic_b200_sim_t *s)
 	}
 	if(s->comm)
 	{
-		int rc = comm_rho_halo(s->comm, s->rho, s->stream, &s->launches);
+		int rc = comm_rho_halo(s->comm, s->rho, s->stream, s->errflag, &s->launches);
 		if(rc) return rc;
 	}
 	else if(!set.n)
@@ -1394,6 +1415,7 @@ cpic_b200_sync(cpic_b200_sim_t *s)
 	if(!e) return check_capacity(s);
 	CK(cudaMemsetAsync(s->errflag, 0, sizeof(int), s->stream));
 	if(e & ERRBIT_TMA) return fail(CPIC_B200_ECUDA, "a TMA tile load did not complete (tensor map rejected)");
+	if(e & ERRBIT_PEER) return fail(CPIC_B200_ECUDA, "a neighbour rank did not arrive at an exchange (peer-memory handshake timed out)");
 	if(e & ERRBIT_VELOCITY) return fail(CPIC_B200_EVELOCITY, "Max velocity exceeded (umax = %g %g %g)", s->umax[0], s->umax[1], s->umax[2]);
 	if(e & ERRBIT_FAR) return fail(CPIC_B200_EFAR, "a particle crossed a slab face by more than one particle block row (%d cells) in one step", s->g.BY);
 	return fail(CPIC_B200_ECAPACITY, "capacity exceeded (%s%s%s%s): raise capacity_factor (now %g) / outbox_fraction",
@@ -1619,6 +1641,53 @@ extern "C" void cpic_b200_host_free(void *p) { if(p) cudaFreeHost(p); }
 
 /* ---------------------------------------------------------------- multi-GPU */
 
+/* Peer memory (comm.h): tells the neighbour ranks where this rank's outboxes live now and maps
+ * theirs: pob[north/south][buffer] of every species. Collective -- every rank calls it at the same
+ * points: when the communicator is created and after species storage has changed (capacity growth
+ * agreed over the ranks, the per-particle E arrays at the first staged step). */
+static int
+p2p_attach(sim_t_ *s)
+{
+	Comm *c = s->comm;
+	s->p2p_stale = false;
+	if(!comm_p2p(c)) return 0;
+	for(int is = 0; is < s->p.nspecies; is++)
+	{
+		SpeciesHost &h = s->sp[is];
+		/* mapped again from scratch: a new allocation can sit at the address of the one it replaces */
+		if(comm_p2p_unmap(c, comm_export_species(is, 0)) || comm_p2p_unmap(c, comm_export_species(is, 1)))
+			return CPIC_B200_ECUDA;
+		/* the outboxes are one allocation (two buffers of records + counters); the (E_x, E_y) of the
+		 * records live in the per-particle E allocation */
+		if(comm_p2p_export(c, comm_export_species(is, 0), h.oblock, h.oblock ? 1 : 0)
+				|| comm_p2p_export(c, comm_export_species(is, 1), h.pE, h.pE ? 1 : 0))
+			return CPIC_B200_ECUDA;
+	}
+	if(comm_p2p_refresh(c, s->stream)) return CPIC_B200_ECUDA;
+	const int peer[2] = { comm_rank_north(c), comm_rank_south(c) };
+	for(int is = 0; is < s->p.nspecies; is++)
+	{
+		SpeciesHost &h = s->sp[is];
+		memset(h.d.pob, 0, sizeof(h.d.pob));
+		if(!h.oblock) continue;
+		for(int d = 0; d < 2; d++)
+		{
+			char *ro = (char *) comm_p2p_remote(c, comm_export_species(is, 0), peer[d]);
+			char *re = (char *) comm_p2p_remote(c, comm_export_species(is, 1), peer[d]);
+			if(!ro) return fail(CPIC_B200_EINVAL, "rank %d has no storage for species %d: every rank must hold every species", peer[d], is);
+			if(h.pE && !re) return fail(CPIC_B200_EINVAL, "rank %d keeps no per-particle E for species %d", peer[d], is);
+			for(int k = 0; k < 2; k++)
+			{
+				/* equal capacities on all ranks (cpic_b200_capacity): the neighbours' layout is this rank's */
+				h.d.pob[d][k].rec = (double *) (ro + ((char *) h.d.ob[k].rec - (char *) h.oblock));
+				h.d.pob[d][k].count = (int *) (ro + ((char *) h.d.ob[k].count - (char *) h.oblock));
+				h.d.pob[d][k].recE = h.d.ob[k].recE ? (double *) (re + ((char *) h.d.ob[k].recE - (char *) h.pE)) : NULL;
+			}
+		}
+	}
+	return 0;
+}
+
 extern "C" int
 cpic_b200_comm_id(void *id128)
 {
@@ -1635,5 +1704,10 @@ cpic_b200_comm_init(cpic_b200_sim_t *s, const void *id128)
 	if(s->comm) return fail(CPIC_B200_EINVAL, "communicator already initialised");
 	s->comm = comm_create(id128, s->p.rank, s->p.nranks, s->g, s->stream, g_err, sizeof(g_err));
 	if(!s->comm) return CPIC_B200_ECUDA;
+	if(comm_p2p(s->comm))
+	{
+		if(comm_p2p_export(s->comm, COMM_EXPORT_PHI, s->phi, (size_t) (s->g.ny + 3) * s->g.S * sizeof(double))) return CPIC_B200_ECUDA;
+		return p2p_attach(s);
+	}
 	return 0;
 }

@@ -161,6 +161,16 @@ template <typename F> static inline cudaError_t cudaOccupancyMaxActiveBlocksPerM
 	return cudaSuccess;
 }
 
+/* no peer memory between the processes of the CPU test suite: the multi-rank tests take the NCCL path */
+struct cudaIpcMemHandle_t { char reserved[64]; };
+enum { cudaIpcMemLazyEnablePeerAccess = 1 };
+static inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *, void *) { return cudaErrorInvalidValue; }
+static inline cudaError_t cudaIpcOpenMemHandle(void **, cudaIpcMemHandle_t, unsigned) { return cudaErrorInvalidValue; }
+static inline cudaError_t cudaIpcCloseMemHandle(void *) { return cudaErrorInvalidValue; }
+static inline void __threadfence_system() {}
+static inline long long clock64() { return 0; }
+static inline void __nanosleep(unsigned) {}
+
 /* ---- driver API: tensor maps ---- */
 typedef int CUresult;
 enum { CUDA_SUCCESS = 0, CUDA_ERROR_INVALID_VALUE = 1 };
