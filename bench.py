@@ -515,7 +515,9 @@ def multi_rank_check(env, steps=12):
         # total charge: sum of rho over the slabs (ghost row excluded) against the single-rank sum
         qa = env.reduce(float(many.field("rho")[:nyl].sum()), "sum")
         qb = float(one.field("rho").sum())
-        worst["charge"] = max(worst.get("charge", 0.0), abs(qa - qb) / max(abs(qb), 1e-300))
+        # relative to the charge of one sign (the plasma is neutral: the total itself is ~0)
+        each = sum(abs(q) for q in common["q"]) * n / common["e0"]
+        worst["charge"] = max(worst.get("charge", 0.0), abs(qa - qb) / each)
 
     compare("after sim_init")
     for it in range(steps):

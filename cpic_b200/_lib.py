@@ -65,6 +65,8 @@ EXPORTS = {
     "cpic_b200_occupancy": (_i, [_vp, _i, C.POINTER(_i64 * 6)]),
     "cpic_b200_num_particles": (_i64, [_vp, _i]),
     "cpic_b200_get_particles": (_i64, [_vp, _i, _i64] + [_vp] * 8),
+    "cpic_b200_set_host_order": (_i, [_vp, _i, _i64, _vp]),
+    "cpic_b200_get_particles_ordered": (_i, [_vp, _i, _i64] + [_vp] * 7),
     "cpic_b200_init_uniform": (_i, [_vp, _i, _i64, _i64, _d, _d, C.c_uint64]),
     "cpic_b200_init_beam": (_i, [_vp, _i, _i64, _i64, _d, _d, _d, _d, C.c_uint64]),
     "cpic_b200_stage_field_E": (_i, [_vp]),

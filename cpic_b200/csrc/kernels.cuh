@@ -1331,6 +1331,32 @@ k_image_copy(SpeciesDev sp, int nb, const int *__restrict__ cnt, const long long
 	if(pack <= 0 && lane == 0) sp.count[b] = at + c;
 }
 
+/* Particles in the HOST's order (the drop-in binding keeps the reference's lists, which never
+ * reorder): pos[id] is the place of particle `id` in the host's walk over its lists; entry
+ * pos[id] of each of the seven output arrays (x y ux uy uz E_x E_y, n values each) receives the
+ * particle. The permutation is made here, so that the host writes its lists front to back. */
+static __global__ void __launch_bounds__(256)
+k_gather_ordered(SpeciesDev sp, int nb, const int *__restrict__ pos, long long npos, double *__restrict__ out,
+		long long n, int *__restrict__ errflag)
+{
+	const int lane = threadIdx.x & 31;
+	const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	if(b >= nb) return;
+	const int c = sp.count[b];
+	for(int i = lane; i < c; i += 32)
+	{
+		const seg_index_t q = seg_slot(sp.cap, b, i);
+		const long long id = sp.id[q];
+		const long long p = (id >= 0 && id < npos) ? pos[id] : -1;
+		if(p < 0 || p >= n) { atomicOr(errflag, 1); continue; }
+		out[p] = sp.x[q]; out[n + p] = sp.y[q];
+		out[2 * n + p] = sp.ux[q]; out[3 * n + p] = sp.uy[q]; out[4 * n + p] = sp.uz[q];
+		const size_t e = (size_t) b * sp.cap + i;
+		out[5 * n + p] = sp.pEx ? sp.pEx[e] : 0.0;
+		out[6 * n + p] = sp.pEy ? sp.pEy[e] : 0.0;
+	}
+}
+
 /* Kinetic energy per species: sum(ux^2 + uy^2), reference src/sim.c:366-395 (compiled
  * out there). One warp per block, fixed order; block sums land in out[b]. */
 static __global__ void __launch_bounds__(256)

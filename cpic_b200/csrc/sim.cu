@@ -63,6 +63,8 @@ struct SpeciesHost {
 	std::vector<int> *tally; /* per-block counts of a streamed initialisation (count_particles / add_particles) */
 	double *pE;              /* optional per-particle E (segment and outboxes) */
 	int arr;                 /* outbox that holds the pending arrivals */
+	int *hpos;               /* id -> place in the host's own order (cpic_b200_set_host_order) */
+	long long hpos_n, horder_n;
 	long long n;
 	double q, m;
 };
@@ -359,8 +361,11 @@ free_species(SpeciesHost &h)
 	double q = h.q, m = h.m;
 	int reserve = h.reserve;
 	std::vector<int> *tally = h.tally;
+	int *hpos = h.hpos;          /* the host's order outlives a change of the device layout */
+	long long hpos_n = h.hpos_n, horder_n = h.horder_n;
 	memset(&h, 0, sizeof(h));
 	h.q = q; h.m = m; h.reserve = reserve; h.tally = tally;
+	h.hpos = hpos; h.hpos_n = hpos_n; h.horder_n = horder_n;
 }
 
 extern "C" void
@@ -374,6 +379,8 @@ cpic_b200_destroy(cpic_b200_sim_t *s)
 		free_species(s->sp[i]);
 		delete s->sp[i].tally;
 		s->sp[i].tally = NULL;
+		cudaFree(s->sp[i].hpos);
+		s->sp[i].hpos = NULL;
 	}
 	if(s->comm) comm_destroy(s->comm);
 	if(s->have_plans) { cufftDestroy(s->plan_fwd); cufftDestroy(s->plan_inv); }
@@ -1008,6 +1015,62 @@ cpic_b200_get_particles(cpic_b200_sim_t *s, int is, int64_t capn, int64_t *id, d
 		}
 	}
 	return n;
+}
+
+/* Host lists that keep their own order (the drop-in binding, dropin/cpic_b200_stages.c): `ids` are the
+ * particle ids in the order the host walks its lists */
+extern "C" int
+cpic_b200_set_host_order(cpic_b200_sim_t *s, int is, int64_t n, const int64_t *ids)
+{
+	if(!s || is < 0 || is >= s->p.nspecies || n < 0 || (n && !ids)) return fail(CPIC_B200_EINVAL, "bad species or ids");
+	CK(cudaSetDevice(s->device));
+	SpeciesHost &h = s->sp[is];
+	int64_t maxid = -1;
+	for(int64_t k = 0; k < n; k++)
+	{
+		if(ids[k] < 0 || ids[k] >= (1LL << 31)) return fail(CPIC_B200_EINVAL, "particle id %lld out of range", (long long) ids[k]);
+		maxid = std::max(maxid, ids[k]);
+	}
+	std::vector<int> pos((size_t) (maxid + 1), -1);
+	for(int64_t k = 0; k < n; k++) pos[(size_t) ids[k]] = (int) k;
+	cudaFree(h.hpos);
+	h.hpos = NULL;
+	h.hpos_n = maxid + 1;
+	h.horder_n = n;
+	if(maxid >= 0)
+	{
+		CK(cudaMalloc(&h.hpos, pos.size() * sizeof(int)));
+		CK(cudaMemcpy(h.hpos, pos.data(), pos.size() * sizeof(int), cudaMemcpyHostToDevice));
+	}
+	return 0;
+}
+
+/* The particles of one species in the order given to cpic_b200_set_host_order: entry k of every array
+ * belongs to ids[k]. Any pointer may be NULL; pinned arrays (cpic_b200_host_alloc) are filled by DMA. */
+extern "C" int
+cpic_b200_get_particles_ordered(cpic_b200_sim_t *s, int is, int64_t n, double *x, double *y,
+		double *ux, double *uy, double *uz, double *Ex, double *Ey)
+{
+	if(!s || is < 0 || is >= s->p.nspecies) return fail(CPIC_B200_EINVAL, "bad species");
+	CK(cudaSetDevice(s->device));
+	SpeciesHost &h = s->sp[is];
+	if(n != h.horder_n) return fail(CPIC_B200_EINVAL, "species %d: %lld particles asked for, the host order holds %lld", is,
+			(long long) n, (long long) h.horder_n);
+	if(n == 0 || !h.block) return 0;
+	int rc = absorb(s, is);
+	if(rc) return rc;
+	if((rc = image_staging(s, (size_t) 7 * (size_t) n))) return rc;
+	int *flag = s->errflag + 14;
+	CK(cudaMemsetAsync(flag, 0, sizeof(int), s->stream));
+	k_gather_ordered<<<(s->nb + 7) / 8, 256, 0, s->stream>>>(h.d, s->nb, h.hpos, h.hpos_n, s->img, n, flag);
+	CK(cudaGetLastError());
+	double *outs[7] = { x, y, ux, uy, uz, Ex, Ey };
+	for(int a = 0; a < 7; a++)
+		if(outs[a]) CK(cudaMemcpyAsync(outs[a], s->img + (size_t) a * (size_t) n, (size_t) n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+	CK(cudaMemcpyAsync(s->h_err + 14, flag, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+	CK(cudaStreamSynchronize(s->stream));
+	if(s->h_err[14]) return fail(CPIC_B200_EINVAL, "species %d holds a particle whose id is not in the host order", is);
+	return 0;
 }
 
 /* ------------------------------------------------------------------ timing */

@@ -14,9 +14,11 @@
  * it on demand.
  */
 #define _GNU_SOURCE
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #include "sim.h"
 #include "field.h"
@@ -31,8 +33,11 @@ typedef struct slot { ppack_t *p; int lane; } slot_t;
 static struct {
 	sim_t *sim;
 	cpic_b200_sim_t *gpu;
-	slot_t **slots;          /* per species: id -> host slot */
+	slot_t **slots;          /* per species: host slot of the k-th particle of the walk over the lists */
+	i64 *count;              /* per species: particles in the lists */
+	double *stage[7];        /* pinned: x y ux uy uz E_x E_y of one species, in walk order */
 	int lazy;
+	int threads;
 } D;
 
 static void
@@ -79,6 +84,14 @@ attach(sim_t *sim)
 	D.sim = sim;
 	D.lazy = getenv("CPIC_B200_SYNC") && strcmp(getenv("CPIC_B200_SYNC"), "lazy") == 0;
 	D.slots = calloc((size_t) sim->nspecies, sizeof(slot_t *));
+	D.count = calloc((size_t) sim->nspecies, sizeof(i64));
+	i64 nstage = 0;
+	{
+		long nc = sysconf(_SC_NPROCESSORS_ONLN);
+		D.threads = nc < 1 ? 1 : (nc > 16 ? 16 : (int) nc);
+		if(getenv("CPIC_B200_SYNC_THREADS")) D.threads = atoi(getenv("CPIC_B200_SYNC_THREADS"));
+		if(D.threads < 1) D.threads = 1;
+	}
 
 	for(is = 0; is < sim->nspecies; is++)
 	{
@@ -87,7 +100,7 @@ attach(sim_t *sim)
 		double *x = malloc((size_t) nmax * sizeof(double)), *y = malloc((size_t) nmax * sizeof(double));
 		double *ux = malloc((size_t) nmax * sizeof(double)), *uy = malloc((size_t) nmax * sizeof(double));
 		double *uz = malloc((size_t) nmax * sizeof(double));
-		D.slots[is] = calloc((size_t) nmax, sizeof(slot_t));
+		D.slots[is] = calloc((size_t) nmax + 1, sizeof(slot_t));
 		for(ic = 0; ic < sim->plasma.nchunks; ic++)
 		{
 			pblock_t *b;
@@ -100,14 +113,24 @@ attach(sim_t *sim)
 						id[k] = pk->i[iv];
 						x[k] = pk->r[X][iv]; y[k] = pk->r[Y][iv];
 						ux[k] = pk->u[X][iv]; uy[k] = pk->u[Y][iv]; uz[k] = pk->u[Z][iv];
-						D.slots[is][pk->i[iv]].p = pk;
-						D.slots[is][pk->i[iv]].lane = (int) iv;
+						D.slots[is][k].p = pk;
+						D.slots[is][k].lane = (int) iv;
 						k++;
 					}
 		}
 		n = k;
+		D.count[is] = n;
+		if(n > nstage) nstage = n;
 		if(cpic_b200_set_particles(D.gpu, (int) is, n, (const int64_t *) id, x, y, ux, uy, uz)) fatal("set_particles");
+		/* the lists never reorder on the host (comm_plasma runs on the device): downloads come back
+		 * in this walk's order */
+		if(cpic_b200_set_host_order(D.gpu, (int) is, n, (const int64_t *) id)) fatal("set_host_order");
 		free(id); free(x); free(y); free(ux); free(uy); free(uz);
+	}
+	for(int k = 0; k < 7; k++)
+	{
+		D.stage[k] = cpic_b200_host_alloc((size_t) (nstage + 1) * sizeof(double));
+		if(!D.stage[k]) fatal("pinned staging");
 	}
 }
 
@@ -126,30 +149,49 @@ sync_fields(sim_t *sim)
 	if(cpic_b200_get_field(D.gpu, CPIC_B200_EY, f->_E[Y]->data)) fatal("get E_Y");
 }
 
-/* SoA -> plist (by particle id) and grids -> mat_t */
+/* One thread's share of the walk: entry k of the staged arrays into the k-th slot of the lists */
+typedef struct fill_job { const slot_t *slots; i64 k0, k1; } fill_job_t;
+
+static void *
+fill_lists(void *arg)
+{
+	const fill_job_t *j = arg;
+	for(i64 k = j->k0; k < j->k1; k++)
+	{
+		const slot_t s = j->slots[k];
+		s.p->r[X][s.lane] = D.stage[0][k]; s.p->r[Y][s.lane] = D.stage[1][k];
+		s.p->u[X][s.lane] = D.stage[2][k]; s.p->u[Y][s.lane] = D.stage[3][k]; s.p->u[Z][s.lane] = D.stage[4][k];
+		s.p->E[X][s.lane] = D.stage[5][k]; s.p->E[Y][s.lane] = D.stage[6][k];
+	}
+	return NULL;
+}
+
+/* SoA -> plist and grids -> mat_t. The device permutes the particles into the order of the host's
+ * lists and copies them into pinned staging arrays (cpic_b200_get_particles_ordered); the lists are
+ * then written front to back by a few threads. */
 void
 cpic_b200_dropin_sync(sim_t *sim)
 {
-	i64 is, k;
+	i64 is;
 
 	if(!D.gpu) return;
 	for(is = 0; is < sim->nspecies; is++)
 	{
-		i64 nmax = sim->species[is].nparticles, n;
-		i64 *id = malloc((size_t) nmax * sizeof(i64));
-		double *a[7];
-		for(k = 0; k < 7; k++) a[k] = malloc((size_t) nmax * sizeof(double));
-		n = cpic_b200_get_particles(D.gpu, (int) is, nmax, (int64_t *) id, a[0], a[1], a[2], a[3], a[4], a[5], a[6]);
-		if(n < 0 || n > nmax) fatal("get_particles");
-		for(k = 0; k < n; k++)
+		const i64 n = D.count[is];
+		if(cpic_b200_get_particles_ordered(D.gpu, (int) is, n, D.stage[0], D.stage[1], D.stage[2], D.stage[3],
+					D.stage[4], D.stage[5], D.stage[6])) fatal("get_particles_ordered");
+		int nt = n < 65536 ? 1 : D.threads;
+		pthread_t th[16];
+		fill_job_t job[16];
+		for(int t = 0; t < nt; t++)
 		{
-			slot_t s = D.slots[is][id[k]];
-			s.p->r[X][s.lane] = a[0][k]; s.p->r[Y][s.lane] = a[1][k];
-			s.p->u[X][s.lane] = a[2][k]; s.p->u[Y][s.lane] = a[3][k]; s.p->u[Z][s.lane] = a[4][k];
-			s.p->E[X][s.lane] = a[5][k]; s.p->E[Y][s.lane] = a[6][k];
+			job[t].slots = D.slots[is];
+			job[t].k0 = n * t / nt;
+			job[t].k1 = n * (t + 1) / nt;
+			if(t > 0 && pthread_create(&th[t], NULL, fill_lists, &job[t])) { fill_lists(&job[t]); th[t] = 0; }
 		}
-		free(id);
-		for(k = 0; k < 7; k++) free(a[k]);
+		fill_lists(&job[0]);
+		for(int t = 1; t < nt; t++) if(th[t]) pthread_join(th[t], NULL);
 	}
 	sync_fields(sim);
 }

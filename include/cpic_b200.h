@@ -115,6 +115,16 @@ int64_t cpic_b200_get_particles(cpic_b200_sim_t *sim, int species, int64_t cap,
 		int64_t *id, double *x, double *y, double *ux, double *uy, double *uz,
 		double *Ex, double *Ey);
 
+/* Host lists that keep their own order -- the reference's plist/pblock/ppack lists (src/def.h:88-211),
+ * which the drop-in binding refreshes after a step and which never reorder there because comm_plasma
+ * runs on the device. cpic_b200_set_host_order takes the particle ids in the order the host walks its
+ * lists; cpic_b200_get_particles_ordered then fills arrays whose entry k belongs to ids[k]: the
+ * permutation from particle-block order is made on the device and the host writes its lists front to
+ * back. Arrays from cpic_b200_host_alloc (pinned) are filled by DMA. Any array may be NULL. */
+int cpic_b200_set_host_order(cpic_b200_sim_t *sim, int species, int64_t n, const int64_t *ids);
+int cpic_b200_get_particles_ordered(cpic_b200_sim_t *sim, int species, int64_t n, double *x, double *y,
+		double *ux, double *uy, double *uz, double *Ex, double *Ey);
+
 /* Throughput-only initialiser on the device (no host arrays): uniform positions,
  * u ~ U(-v, v) per axis like "random position" (src/particle.c:23-89) but from a
  * counter-based generator, not glibc rand(). n is this rank's share. */

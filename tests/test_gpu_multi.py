@@ -35,10 +35,30 @@ def test_two_ranks(conf, mode):
     run_ranks(2, conf, 10, mode)
 
 
-def test_four_ranks():
+@pytest.mark.parametrize("conf,mode,env", [("uniform-small.conf", "fused", None), ("far-beam-tall.conf", "fused", None),
+                                          ("2d-2species-small.conf", "staged", None),
+                                          ("uniform-small.conf", "fused", {"MGPU_RUN": "1"})])
+def test_four_ranks(conf, mode, env):
     if ngpus() < 4:
         pytest.skip("needs 4 GPUs")
-    run_ranks(4, "uniform-small.conf", 10, "fused", port=29613)
+    run_ranks(4, conf, 12, mode, port=29613, env=env)
+
+
+@pytest.mark.parametrize("conf,mode,env", [("uniform-tall.conf", "fused", None), ("far-beam-tall.conf", "fused", None),
+                                          ("uniform-tall.conf", "staged", None),
+                                          ("uniform-tall.conf", "fused", {"MGPU_RUN": "1", "MGPU_TIGHT": "1"})])
+def test_eight_ranks(conf, mode, env):
+    if ngpus() < 8:
+        pytest.skip("needs 8 GPUs")
+    run_ranks(8, conf, 12 if not env else 40, mode, port=29617, env=env)
+
+
+def test_two_ranks_over_nccl():
+    """The same exchange without peer memory (CPIC_B200_P2P=0): the face regions, halos and FFT transposes
+    travel by NCCL send/recv."""
+    if ngpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    run_ranks(2, "far-beam.conf", 10, "fused", port=29619, env={"CPIC_B200_P2P": "0"})
 
 
 def test_two_ranks_capacity_growth():

@@ -119,12 +119,45 @@ def test_reference_drivers_through_the_dropin_under_the_interpreter(simt_build):
     run_under_interpreter(simt_build, ["tests/test_gpu_dropin.py", "-k", "cyclotron or cli_and_output"])
 
 
-def test_bench_call_sequence_under_the_interpreter(simt_build):
-    """tests/simt/bench_sequence.py: every C-ABI call bench.py makes, in its order, at a small size."""
-    env = dict(os.environ, CPIC_B200_LIB=simt_build, CPIC_B200_SIMT_CHECK="1")
-    r = subprocess.run([sys.executable, os.path.join(SIMT, "bench_sequence.py")], cwd=ROOT, env=env,
-                       capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0 and "DRY RUN OK" in r.stdout, (r.stdout + r.stderr)[-3000:]
+def test_bench_script_under_the_interpreter(simt_build):
+    """bench.py itself, every leg of its default run (main workload, per-stage pass, staged stages, C-ABI e2e,
+    the other workloads, the multi-process CPU reference), at a tiny size (BENCH_TINY) against the
+    interpreted kernels: the one JSON line must parse and carry the contract's keys."""
+    import json
+    env = dict(os.environ, CPIC_B200_LIB=simt_build, CPIC_B200_SIMT_CHECK="1", BENCH_TINY="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "3", "--warmup", "3"], cwd=ROOT, env=env,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout[-2000:]
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert k in d, k
+    assert d["config"]["workload"].startswith("D:") and d["gpu_launches"] > 0
+    assert set(d["other_workloads"]) == {"A", "2s"} and all("value" in v for v in d["other_workloads"].values())
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert k in d["roofline"], k
+    if d["cpu_baseline"]["kind"] == "reference":
+        assert d["cpu_baseline"]["cores"] >= 1
+
+
+def test_bench_reference_arm(simt_build):
+    """`bench.py --impl reference` (the unmodified reference over forked ranks, oracle/_ref/cpic_ref_mp) at
+    the tiny size: one JSON line with impl, cpu_baseline and e2e; no product library is imported."""
+    import json
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "cpic_ref_mp")):
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+    env = dict(os.environ, BENCH_TINY="1")
+    env.pop("CPIC_B200_LIB", None)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "4", "--warmup", "3"],
+                       cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "reference" and d["value"] > 0
+    assert d["warmup"] == 3 and d["steps"] == 4
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["config"]["workload"].startswith("D:")
 
 
 def test_physics_under_the_interpreter(simt_build):

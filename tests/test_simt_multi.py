@@ -70,3 +70,21 @@ def test_run_and_run_timed_on_two_ranks_on_cpu(simt_build):
     out = run_ranks_cpu(simt_build, 2, "uniform-small.conf", 70, env={"MGPU_RUN": "1", "MGPU_TIGHT": "1"}, timeout=900)
     assert "MGPU-CAPS" in out
 
+
+
+def test_bench_script_on_two_ranks_on_cpu(simt_build):
+    """bench.py with two ranks at the tiny size: the multi_rank_check of the line (N ranks against one rank,
+    product only) and the weak-scaling workload over the multi-rank path."""
+    import json
+    base = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(free_port()), WORLD_SIZE="2", BENCH_TINY="1",
+                CPIC_B200_LIB=simt_build, CPIC_B200_SIMT_CHECK="1",
+                CPIC_B200_NCCL=os.path.join(SIMT, "_build", "libfake_nccl.so"))
+    procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "bench.py"), "--gpus", "2", "--steps", "3", "--warmup", "3",
+                               "--no-e2e"], env=dict(base, RANK=str(r), LOCAL_RANK=str(r)), cwd=ROOT,
+                              stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=900) for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(o[1][-2000:] for o in outs)
+    d = json.loads(outs[0][0].strip().splitlines()[-1])
+    assert d["n_gpus"] == 2 and d["multi_rank_check"]["ok"] and d["multi_rank_check"]["worst"] <= 1e-12
+    assert d["multi_rank_check"]["count_conserved"] and d["multi_rank_check"]["particles_on_another_rank_than_at_start"] > 0
+    assert outs[1][0].strip() == ""          # rank 0 alone prints
