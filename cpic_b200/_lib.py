@@ -98,6 +98,8 @@ EXPORTS = {
     "cpic_b200_conf_init_particles": (_i, [_vp, _i] + [_pp] * 5),
     "cpic_b200_sim_from_conf": (_i, [C.c_char_p, _i, _i, _i, _i, _pp, C.POINTER(RunC)]),
     "cpic_b200_sim_from_conf_streamed": (_i, [C.c_char_p, _i, _i, _i, _i, _i64, _pp, C.POINTER(RunC)]),
+    "cpic_b200_sim_from_conf_device": (_i, [C.c_char_p, _i, _i, _i, _i, _i64, _pp, C.POINTER(RunC)]),
+    "cpic_b200_init_reference": (_i, [_vp, _i, _vp, _i64]),
     "cpic_b200_conf_stream_particles": (_i, [_vp, _i, _i64, _vp, _vp]),
     "cpic_b200_write_fields": (_i, [_vp, C.c_char_p, _i64, _i64, _i64, _i64, _d, _d]),
     "cpic_b200_main": (_i, [_i, C.POINTER(C.c_char_p)]),

@@ -358,6 +358,66 @@ cpic_b200_sim_from_conf_streamed(const char *path, int rank, int nranks, int dev
 	return 0;
 }
 
+/* sim_init with the reference's initial conditions drawn on the device: the runs of
+ * generate_particles (process -> chunk -> species) handed to cpic_b200_init_reference */
+extern "C" int
+cpic_b200_sim_from_conf_device(const char *path, int rank, int nranks, int device, int ref_nprocs,
+		int64_t batch, cpic_b200_sim_t **out, cpic_b200_run_t *run)
+{
+	cpic_b200_conf_t *c = NULL;
+	cpic_b200_params_t p;
+	cpic_b200_run_t local;
+	if(!run) run = &local;
+	if(ref_nprocs < 1) ref_nprocs = 1;
+	int rc = cpic_b200_conf_load(path, &c);
+	if(rc) return rc;
+	rc = cpic_b200_conf_params(c, rank, nranks, device, &p, run);
+	if(rc) { cpic_b200_conf_free(c); return rc; }
+	conf_node_t *species = conf_lookup(c->root, "species");
+	const long long nchunks = p.plasma_chunks, step = (long long) ref_nprocs * nchunks;
+	std::vector<cpic_b200_init_run_t> runs;
+	for(int proc = 0; proc < ref_nprocs && !rc; proc++)
+	{
+		long long draws = 0;              /* rand() calls of this process so far */
+		for(long long ic = 0; ic < nchunks && !rc; ic++)
+			for(int is = 0; is < p.nspecies && !rc; is++)
+			{
+				conf_node_t *sn = conf_elem(species, is);
+				const char *method = NULL;
+				cpic_b200_init_run_t r;
+				memset(&r, 0, sizeof(r));
+				if(!conf_get_string(conf_member(sn, "init_method"), &method))
+				{ front_set_error("Particle init method for specie %d not specified.", is); rc = CPIC_B200_EINVAL; break; }
+				if(array_float(conf_member(sn, "drift_velocity"), r.v, 2, "drift_velocity")) { rc = CPIC_B200_EINVAL; break; }
+				if(strcmp(method, "random position") == 0) r.method = 0;
+				else if(strcmp(method, "position delta") == 0)
+				{
+					r.method = 1;
+					if(array_float(conf_member(sn, "position_delta"), r.dr, 2, "position_delta")
+							|| array_float(conf_member(sn, "position_init"), r.r0, 2, "position_init")) { rc = CPIC_B200_EINVAL; break; }
+				}
+				else { front_set_error("Unknown init method \"%s\", aborting.", method); rc = CPIC_B200_EINVAL; break; }
+				r.species = is;
+				r.first = ic * ref_nprocs + proc;              /* src/plasma.c:63 */
+				r.step = step;
+				r.count = r.first < run->nparticles[is] ? (run->nparticles[is] - r.first + step - 1) / step : 0;
+				r.seed = run->seed + (unsigned int) proc;       /* src/sim.c:153 */
+				r.draw0 = draws;
+				if(r.method == 0) draws += 4 * r.count;
+				if(r.count > 0) runs.push_back(r);
+			}
+	}
+	cpic_b200_conf_free(c);
+	cpic_b200_sim_t *sim = NULL;
+	if(!rc) rc = cpic_b200_create(&p, &sim);
+	if(rc) return rc;
+	rc = cpic_b200_init_reference(sim, (int) runs.size(), runs.data(), batch);
+	if(!rc && nranks == 1) rc = cpic_b200_pre_step(sim);
+	if(rc) { cpic_b200_destroy(sim); return rc; }
+	*out = sim;
+	return 0;
+}
+
 extern "C" int
 cpic_b200_sim_from_conf(const char *path, int rank, int nranks, int device, int ref_nprocs,
 		cpic_b200_sim_t **out, cpic_b200_run_t *run)

@@ -1414,6 +1414,112 @@ k_sum(const double *__restrict__ in, int n, double *__restrict__ out)
 	if(threadIdx.x == 0) *out = part[0];
 }
 
+/* ---- the reference's own initial conditions, drawn on the device ----
+ * One run = the particles one (process, chunk, species) triple of the reference initialises in one
+ * go (src/plasma.c:292-316, src/particle.c:178-213): ids first, first+step, ...; "random position"
+ * draws four rand() values per particle (x, y, ux, uy: src/particle.c:69-73) from the process's glibc
+ * stream, "position delta" places particle i at WRAP(r0 + dr*i, L) with the drift velocity
+ * (src/particle.c:150-158). Every thread takes REFINIT_K consecutive particles of the run; the host
+ * hands it the state of the generator at its first draw (host/glibc_rand.h: the recurrence
+ * r[i] = r[i-31] + r[i-3] advanced by matrix powers). Bit for bit the values of the host
+ * initialiser (host/front.cpp: generate_particles). */
+#define REFINIT_K 256
+#define REFINIT_THREADS 128
+struct RefInitRun {
+	int method;              /* 0 "random position", 1 "position delta" */
+	long long first, step;   /* particle ids of the run */
+	double v[2], dr[2], r0[2];
+	double Lx, Ly;
+};
+
+static __global__ void __launch_bounds__(REFINIT_THREADS)
+k_refinit_generate(RefInitRun run, long long k0, long long n, const unsigned *__restrict__ states,
+		double *__restrict__ x, double *__restrict__ y, double *__restrict__ ux, double *__restrict__ uy,
+		long long *__restrict__ id)
+{
+	__shared__ unsigned buf[31][REFINIT_THREADS];
+	const int tid = threadIdx.x;
+	const long long t = (long long) blockIdx.x * blockDim.x + tid;
+	const long long j0 = t * REFINIT_K;
+	if(j0 >= n) return;
+	if(run.method == 0)
+		for(int i = 0; i < 31; i++) buf[i][tid] = states[t * 31 + i];
+	int p = 0;                       /* buf[p]: the oldest of the last 31 values */
+	auto draw = [&]() -> double
+	{
+		const int q = p + 28 >= 31 ? p - 3 : p + 28;
+		const unsigned v = buf[p][tid] + buf[q][tid];
+		buf[p][tid] = v;
+		p = p == 30 ? 0 : p + 1;
+		/* rand() / (RAND_MAX + 1.0): exact */
+		return (double) (v >> 1) * (1.0 / 2147483648.0);
+	};
+	const long long j1 = j0 + REFINIT_K < n ? j0 + REFINIT_K : n;
+	for(long long j = j0; j < j1; j++)
+	{
+		const long long i = run.first + (k0 + j) * run.step;
+		double px, py, pux, puy;
+		if(run.method == 0)
+		{
+			/* uniform(a, b) = rand() / (RAND_MAX + 1.0) * (b - a) + a, src/particle.c:17-21 */
+			px = ADD(MUL(draw(), SUB(run.Lx, 0.0)), 0.0);
+			py = ADD(MUL(draw(), SUB(run.Ly, 0.0)), 0.0);
+			pux = ADD(MUL(draw(), SUB(run.v[0], -run.v[0])), -run.v[0]);
+			puy = ADD(MUL(draw(), SUB(run.v[1], -run.v[1])), -run.v[1]);
+		}
+		else
+		{
+			/* the reference build fuses r0 + dr*i (see host/front.cpp) */
+			px = fmod(FMA(run.dr[0], (double) i, run.r0[0]), run.Lx);
+			if(px < 0.0) px = ADD(px, run.Lx);
+			py = fmod(FMA(run.dr[1], (double) i, run.r0[1]), run.Ly);
+			if(py < 0.0) py = ADD(py, run.Ly);
+			pux = run.v[0]; puy = run.v[1];
+		}
+		x[j] = px; y[j] = py; ux[j] = pux; uy[j] = puy; id[j] = i;
+	}
+}
+
+/* Particle block of every particle of a batch: over all slabs (tally: capacity, pass 1) or inside
+ * this rank's slab (key, value = position in the batch; a particle of another slab gets key nb) */
+static __global__ void
+k_refinit_keys(const double *__restrict__ x, const double *__restrict__ y, long long n, Geom g, int nb,
+		int *__restrict__ tally, int *__restrict__ key, int *__restrict__ val, int *__restrict__ cnt)
+{
+	const long long j = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	if(j >= n) return;
+	/* what the host binning does with a particle on the upper edge (particle_comm_initial wraps it) */
+	const double px = x[j] >= g.Lx ? x[j] - g.Lx : x[j], py = y[j] >= g.Ly ? y[j] - g.Ly : y[j];
+	const int row = global_row(g, py);
+	const int bxg = cell_ix(g, px) >> g.lBX;
+	if(tally) atomicAdd(&tally[(size_t) (row >> g.lBY) * g.nbx + bxg], 1);
+	if(key)
+	{
+		const bool mine = row >= g.row0 && row < g.row0 + g.ny;
+		const int k = mine ? ((row - g.row0) >> g.lBY) * g.nbx + bxg : nb;
+		key[j] = k;
+		val[j] = (int) j;
+		atomicAdd(&cnt[k], 1);
+	}
+}
+
+/* The batch in block order (val: the stable sort's permutation) as the compact image k_image_copy appends */
+static __global__ void
+k_refinit_gather(const int *__restrict__ val, long long n_in, const double *__restrict__ x, const double *__restrict__ y,
+		const double *__restrict__ ux, const double *__restrict__ uy, const long long *__restrict__ id,
+		double *__restrict__ img, Geom g)
+{
+	const long long j = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	if(j >= n_in) return;
+	const int s = val[j];
+	img[j] = x[s] >= g.Lx ? x[s] - g.Lx : x[s];
+	img[n_in + j] = y[s] >= g.Ly ? y[s] - g.Ly : y[s];
+	img[2 * n_in + j] = ux[s];
+	img[3 * n_in + j] = uy[s];
+	img[4 * n_in + j] = 0.0;
+	img[5 * n_in + j] = __longlong_as_double(id[s]);
+}
+
 /* Throughput-only initialiser: particle k of block b sits uniformly inside block b, so
  * the plasma is uniform with equal block populations; u ~ U(-v, v) per axis as in the
  * reference's "random position" (src/particle.c:72-73), plus a drift (a beam: the

@@ -21,6 +21,12 @@
 #include "cpic_b200.h"
 #include "kernels.cuh"
 #include "comm.h"
+#include "host/glibc_rand.h"
+
+#ifndef CPIC_B200_SIMT_CHECK
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#endif
 
 /* ------------------------------------------------------------------ errors */
 
@@ -744,6 +750,185 @@ cpic_b200_init_beam(cpic_b200_sim_t *s, int is, int64_t n, int64_t id0, double d
 	for(int k = 0; k < 2; k++) CK(cudaMemsetAsync(h.d.ob[k].count, 0, (size_t) s->nob * 9 * sizeof(int), s->stream));
 	h.n = n;
 	return 0;
+}
+
+/* plasma_init with the reference's own initial conditions drawn on the device (the host initialiser
+ * makes four serial rand() calls per particle: minutes for 1e9 particles). Two passes over the runs:
+ * the first tallies every particle per particle block (all slabs: every rank arrives at the same
+ * capacity), the second keeps this rank's slab, sorts every batch by block (stable radix sort: a
+ * block holds its particles in the order they were drawn) and appends it to the segments. */
+struct RefInitScratch {
+	double *x, *y, *ux, *uy;
+	long long *id;
+	unsigned *states;
+	int *key, *val, *key2, *val2, *cnt, *tally;
+	long long *off;
+	void *tmp;
+	size_t tmp_bytes;
+};
+
+static void
+refinit_free(RefInitScratch &w)
+{
+	cudaFree(w.x); cudaFree(w.id); cudaFree(w.states); cudaFree(w.key); cudaFree(w.cnt); cudaFree(w.tally);
+	cudaFree(w.off); cudaFree(w.tmp);
+	memset(&w, 0, sizeof(w));
+}
+
+/* One batch of one run into w.x .. w.id: thread states from `st` (advanced past the batch on return) */
+static int
+refinit_batch(sim_t_ *s, RefInitScratch &w, const cpic_b200_init_run_t &r, long long k0, long long n,
+		uint32_t st[31], const uint32_t stepm[31][31], std::vector<uint32_t> &hstates)
+{
+	const long long nthreads = (n + REFINIT_K - 1) / REFINIT_K;
+	RefInitRun run;
+	run.method = r.method; run.first = r.first; run.step = r.step;
+	for(int d = 0; d < 2; d++) { run.v[d] = r.v[d]; run.dr[d] = r.dr[d]; run.r0[d] = r.r0[d]; }
+	run.Lx = s->g.Lx; run.Ly = s->g.Ly;
+	if(r.method == 0)
+	{
+		hstates.resize((size_t) nthreads * 31);
+		for(long long t = 0; t < nthreads; t++)
+		{
+			memcpy(&hstates[(size_t) t * 31], st, 31 * sizeof(uint32_t));
+			GlibcRandJump::apply(stepm, st);          /* 4 * REFINIT_K draws further */
+		}
+		CK(cudaMemcpyAsync(w.states, hstates.data(), hstates.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s->stream));
+	}
+	k_refinit_generate<<<(unsigned) ((nthreads + REFINIT_THREADS - 1) / REFINIT_THREADS), REFINIT_THREADS, 0, s->stream>>>(
+			run, k0, n, w.states, w.x, w.y, w.ux, w.uy, w.id);
+	CK(cudaGetLastError());
+	/* hstates is overwritten by the next batch */
+	CK(cudaStreamSynchronize(s->stream));
+	return 0;
+}
+
+extern "C" int
+cpic_b200_init_reference(cpic_b200_sim_t *s, int nruns, const cpic_b200_init_run_t *runs, int64_t batch)
+{
+	if(!s || nruns < 0 || (nruns && !runs)) return fail(CPIC_B200_EINVAL, "bad runs");
+	CK(cudaSetDevice(s->device));
+	if(batch < REFINIT_K) batch = 1 << 22;
+	batch = (batch + REFINIT_K - 1) / REFINIT_K * REFINIT_K;
+	if(batch > (1LL << 30)) batch = 1LL << 30;
+	static const GlibcRandJump *J = new GlibcRandJump();
+	uint32_t stepm[31][31];
+	J->power(4ull * REFINIT_K, stepm);
+	const Geom &g = s->g;
+	const size_t nbg = (size_t) g.nbx * g.nby_glob;
+	RefInitScratch w;
+	memset(&w, 0, sizeof(w));
+#define CKW(call) do { cudaError_t e_ = (call); if(e_ != cudaSuccess) { refinit_free(w); \
+	return fail(CPIC_B200_ECUDA, "%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); } } while(0)
+	CKW(cudaMalloc(&w.x, (size_t) batch * 4 * sizeof(double)));
+	w.y = w.x + batch; w.ux = w.y + batch; w.uy = w.ux + batch;
+	CKW(cudaMalloc(&w.id, (size_t) batch * sizeof(long long)));
+	CKW(cudaMalloc(&w.states, (size_t) (batch / REFINIT_K) * 31 * sizeof(unsigned)));
+	CKW(cudaMalloc(&w.key, (size_t) batch * 4 * sizeof(int)));
+	w.val = w.key + batch; w.key2 = w.val + batch; w.val2 = w.key2 + batch;
+	CKW(cudaMalloc(&w.cnt, ((size_t) s->nb + 1) * sizeof(int)));
+	CKW(cudaMalloc(&w.off, ((size_t) s->nb + 1) * sizeof(long long)));
+	std::vector<uint32_t> hstates;
+	int rc = 0;
+	for(int pass = 0; pass < 2 && !rc; pass++)
+	{
+		if(pass == 0)
+		{
+			/* per species: tallies over the blocks of every slab */
+			CKW(cudaMalloc(&w.tally, (size_t) s->p.nspecies * nbg * sizeof(int)));
+			CKW(cudaMemsetAsync(w.tally, 0, (size_t) s->p.nspecies * nbg * sizeof(int), s->stream));
+		}
+		else
+		{
+			for(int is = 0; is < s->p.nspecies && !rc; is++)
+			{
+				SpeciesHost &h = s->sp[is];
+				delete h.tally;
+				h.tally = new std::vector<int>(nbg);
+				CKW(cudaMemcpy(h.tally->data(), w.tally + (size_t) is * nbg, nbg * sizeof(int), cudaMemcpyDeviceToHost));
+				long long total = 0;
+				for(int c : *h.tally) total += c;
+				if(total == 0) { delete h.tally; h.tally = NULL; continue; }
+				rc = cpic_b200_reserve_counted(s, is);
+			}
+			if(rc) break;
+#ifndef CPIC_B200_SIMT_CHECK
+			size_t t1 = 0, t2 = 0;
+			cub::DeviceRadixSort::SortPairs(NULL, t1, w.key, w.key2, w.val, w.val2, (int) batch, 0, 32, s->stream);
+			cub::DeviceScan::ExclusiveSum(NULL, t2, w.cnt, w.off, s->nb + 1, s->stream);
+			w.tmp_bytes = std::max(t1, t2);
+			CKW(cudaMalloc(&w.tmp, w.tmp_bytes));
+#endif
+		}
+		for(int ir = 0; ir < nruns && !rc; ir++)
+		{
+			const cpic_b200_init_run_t &r = runs[ir];
+			if(r.species < 0 || r.species >= s->p.nspecies || r.count < 0 || r.step < 1)
+			{ rc = fail(CPIC_B200_EINVAL, "run %d: bad species, count or step", ir); break; }
+			uint32_t st[31];
+			glibc_rand_seed(r.seed, st);
+			J->jump(st, (uint64_t) r.draw0);
+			SpeciesHost &h = s->sp[r.species];
+			for(long long k0 = 0; k0 < r.count && !rc; k0 += batch)
+			{
+				const long long n = std::min<long long>(batch, r.count - k0);
+				if((rc = refinit_batch(s, w, r, k0, n, st, stepm, hstates))) break;
+				const unsigned grid = (unsigned) ((n + 255) / 256);
+				if(pass == 0)
+				{
+					k_refinit_keys<<<grid, 256, 0, s->stream>>>(w.x, w.y, n, g, s->nb, w.tally + (size_t) r.species * nbg, NULL, NULL, NULL);
+					CKW(cudaGetLastError());
+					continue;
+				}
+#ifdef CPIC_B200_SIMT_CHECK
+				/* the CPU test build has no device sort: the batch is binned by the host path */
+				std::vector<double> hx((size_t) n * 4);
+				std::vector<int64_t> hid((size_t) n);
+				CKW(cudaMemcpy(hx.data(), w.x, (size_t) n * sizeof(double), cudaMemcpyDeviceToHost));
+				CKW(cudaMemcpy(hx.data() + n, w.y, (size_t) n * sizeof(double), cudaMemcpyDeviceToHost));
+				CKW(cudaMemcpy(hx.data() + 2 * n, w.ux, (size_t) n * sizeof(double), cudaMemcpyDeviceToHost));
+				CKW(cudaMemcpy(hx.data() + 3 * n, w.uy, (size_t) n * sizeof(double), cudaMemcpyDeviceToHost));
+				CKW(cudaMemcpy(hid.data(), w.id, (size_t) n * sizeof(int64_t), cudaMemcpyDeviceToHost));
+				std::vector<double> kx, ky, kux, kuy;
+				std::vector<int64_t> kid;
+				for(long long j = 0; j < n; j++)
+				{
+					const double py = hx[(size_t) (n + j)] >= g.Ly ? hx[(size_t) (n + j)] - g.Ly : hx[(size_t) (n + j)];
+					const int row = global_row(g, py);
+					if(row < g.row0 || row >= g.row0 + g.ny) continue;
+					kx.push_back(hx[(size_t) j]); ky.push_back(py);
+					kux.push_back(hx[(size_t) (2 * n + j)]); kuy.push_back(hx[(size_t) (3 * n + j)]);
+					kid.push_back(hid[(size_t) j]);
+				}
+				rc = cpic_b200_add_particles(s, r.species, (int64_t) kid.size(), kid.data(), kx.data(), ky.data(), kux.data(), kuy.data(), NULL);
+#else
+				CKW(cudaMemsetAsync(w.cnt, 0, ((size_t) s->nb + 1) * sizeof(int), s->stream));
+				k_refinit_keys<<<grid, 256, 0, s->stream>>>(w.x, w.y, n, g, s->nb, NULL, w.key, w.val, w.cnt);
+				CKW(cudaGetLastError());
+				int bits = 1;
+				while((1LL << bits) <= s->nb) bits++;
+				size_t tb = w.tmp_bytes;
+				CKW(cub::DeviceRadixSort::SortPairs(w.tmp, tb, w.key, w.key2, w.val, w.val2, (int) n, 0, bits, s->stream));
+				tb = w.tmp_bytes;
+				CKW(cub::DeviceScan::ExclusiveSum(w.tmp, tb, w.cnt, w.off, s->nb + 1, s->stream));
+				long long n_in = 0;
+				CKW(cudaMemcpyAsync(&n_in, w.off + s->nb, sizeof(long long), cudaMemcpyDeviceToHost, s->stream));
+				CKW(cudaStreamSynchronize(s->stream));
+				if(n_in == 0) continue;
+				if((rc = image_staging(s, (size_t) 6 * (size_t) n_in))) break;
+				k_refinit_gather<<<(unsigned) ((n_in + 255) / 256), 256, 0, s->stream>>>(w.val2, n_in, w.x, w.y, w.ux, w.uy, w.id, s->img, g);
+				k_image_copy<<<(s->nb + 7) / 8, 256, 0, s->stream>>>(h.d, s->nb, w.cnt, w.off, s->img, n_in, -1);
+				CKW(cudaGetLastError());
+				CKW(cudaStreamSynchronize(s->stream));
+				h.n += n_in;
+#endif
+			}
+		}
+	}
+#undef CKW
+	/* a block that ended up fuller than its capacity would have been refused by the append */
+	refinit_free(w);
+	return rc;
 }
 
 /* Host view of the fill of one species: counts of the segments and of the regions that hold

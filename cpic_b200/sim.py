@@ -131,13 +131,17 @@ class Sim:
         self.ny_local = self.params.ny // self.params.nranks
 
     @classmethod
-    def from_conf(cls, path, rank=0, nranks=1, device=-1, ref_nprocs=1, stream_batch=0):
+    def from_conf(cls, path, rank=0, nranks=1, device=-1, ref_nprocs=1, stream_batch=0, on_device=False):
         """sim_init (src/sim.c:238-320). stream_batch > 0: the population is generated and uploaded in
-        batches of that many particles (host memory stays small whatever the population)."""
+        batches of that many particles (host memory stays small whatever the population); on_device: the
+        reference's initial conditions are drawn on the GPU (glibc rand() stream by jump-ahead)."""
         L = lib()
         h = C.c_void_p()
         r = RunC()
-        if stream_batch > 0:
+        if on_device:
+            check(L.cpic_b200_sim_from_conf_device(str(path).encode(), rank, nranks, device, ref_nprocs,
+                                                   stream_batch, C.byref(h), C.byref(r)))
+        elif stream_batch > 0:
             check(L.cpic_b200_sim_from_conf_streamed(str(path).encode(), rank, nranks, device, ref_nprocs,
                                                      stream_batch, C.byref(h), C.byref(r)))
         else:

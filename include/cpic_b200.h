@@ -135,6 +135,22 @@ int cpic_b200_init_uniform(cpic_b200_sim_t *sim, int species, int64_t n, int64_t
 int cpic_b200_init_beam(cpic_b200_sim_t *sim, int species, int64_t n, int64_t id0,
 		double dux, double duy, double vx, double vy, uint64_t seed);
 
+/* The reference's own initial conditions drawn on the device. A run is what one (process, chunk,
+ * species) triple of the reference initialises in one go (src/plasma.c:292-316 -> src/particle.c:178-213):
+ * the ids first, first + step, ... (`count` of them); method 0 = "random position" (four rand() calls
+ * per particle from the process's glibc stream: srand(seed), `draw0` calls made before this run),
+ * method 1 = "position delta". Positions and velocities are bit-identical to cpic_b200_conf_init_particles;
+ * inside a particle block the particles are in the order they were drawn. Replaces the populations of
+ * the species the runs name. cpic_b200_sim_from_conf_device builds the runs from a `.conf`. */
+typedef struct cpic_b200_init_run {
+	int32_t species, method;
+	int64_t first, step, count;
+	uint32_t seed;
+	int64_t draw0;
+	double v[2], dr[2], r0[2];
+} cpic_b200_init_run_t;
+int cpic_b200_init_reference(cpic_b200_sim_t *sim, int nruns, const cpic_b200_init_run_t *runs, int64_t batch);
+
 /* ---- the four stages, in sim_step order (src/sim.c:503,517,525,536) ---- */
 int cpic_b200_stage_field_E(cpic_b200_sim_t *sim);     /* src/field.c:450-501 */
 int cpic_b200_stage_plasma_E(cpic_b200_sim_t *sim);    /* src/particle.c:232-248 */
@@ -233,6 +249,10 @@ int cpic_b200_conf_stream_particles(const cpic_b200_conf_t *conf, int ref_nprocs
  * batches whatever the population (the particles are the same ones; inside a particle block they
  * are ordered by batch instead of by id). */
 int cpic_b200_sim_from_conf_streamed(const char *path, int rank, int nranks, int device, int ref_nprocs,
+		int64_t batch, cpic_b200_sim_t **sim, cpic_b200_run_t *run);
+/* The same with the particles drawn on the device (cpic_b200_init_reference): no host arrays, no serial
+ * rand() calls -- 1e9 particles in seconds. */
+int cpic_b200_sim_from_conf_device(const char *path, int rank, int nranks, int device, int ref_nprocs,
 		int64_t batch, cpic_b200_sim_t **sim, cpic_b200_run_t *run);
 /* sim_init (reference src/sim.c:238-320): params, create, host init of all species,
  * upload of this rank's slab, and (single rank only) the pre-step. With several ranks

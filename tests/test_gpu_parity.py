@@ -234,3 +234,23 @@ def test_image_round_trip_is_exact():
         pa, pb = a.particles(i), b.particles(i)
         for k in ("id", "x", "y", "ux", "uy"):
             assert np.array_equal(pa[k], pb[k]), (i, k)
+
+
+@pytest.mark.parametrize("conf,nprocs", [("2d-2species-small.conf", 1), ("uniform-small.conf", 1), ("two-streams.conf", 1),
+                                         ("far-beam.conf", 1), ("2d-2species-small.conf", 4)])
+def test_device_initialiser_draws_the_reference_initial_conditions(conf, nprocs):
+    """cpic_b200_sim_from_conf_device: glibc's rand() stream advanced by matrix powers on the host and
+    drawn on the device in the reference's order (src/particle.c:17-21, 69-73; src/plasma.c:62-128) --
+    bit for bit the particles of the host initialiser, and the same fields after sim_init."""
+    path = conf_path(conf)
+    a = Sim.from_conf(path, ref_nprocs=nprocs)
+    b = Sim.from_conf(path, ref_nprocs=nprocs, on_device=True, stream_batch=4096)
+    for i in range(a.nspecies):
+        pa, pb = a.particles(i), b.particles(i)
+        assert np.array_equal(pa["id"], pb["id"])
+        for k in ("x", "y", "ux", "uy", "uz"):
+            assert np.array_equal(pa[k], pb[k]), (conf, i, k)
+    for k in ("rho", "phi", "Ex", "Ey"):
+        assert relerr(b.field(k), a.field(k)) <= 1e-13, (conf, k)
+    a.close()
+    b.close()
