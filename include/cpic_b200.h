@@ -61,7 +61,7 @@ typedef struct cpic_b200_params {
 	int32_t keep_particle_E;    /* 1: stage_plasma_r also keeps the gathered E per particle */
 	int32_t block_cells;        /* cells per particle-block side (power of two <= 32), 0 = default (8) */
 	double outbox_fraction;     /* exchange buffer per block side as a share of the block capacity,
-	                             * 0 = default (0.5); corners get a quarter of it */
+	                             * 0 = default (0.3); corners get a quarter of it */
 } cpic_b200_params_t;
 
 typedef struct cpic_b200_sim cpic_b200_sim_t;

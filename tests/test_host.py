@@ -141,3 +141,17 @@ def test_cli_usage_and_no_gpu_message():
     if not torch.cuda.is_available():
         r = subprocess.run([cli, "-q", conf_path("cyclotron.conf")], capture_output=True, text=True)
         assert r.returncode == 1 and "no CPU path" in r.stderr
+
+
+def test_glibc_rand_recurrence_and_jump_ahead(tmp_path):
+    """csrc/host/glibc_rand.h restates glibc's rand() (TYPE_3: r[i] = r[i-31] + r[i-3]) so that the device
+    initialiser can draw the reference's initial conditions from any point of the stream: the seeding,
+    5000 values and two jump-aheads (matrix powers) against the C library itself, six seeds."""
+    import subprocess
+    exe = str(tmp_path / "glibc_rand_check")
+    src = os.path.join(ROOT, "tests", "glibc_rand_check.cpp")
+    r = subprocess.run(["g++", "-O2", "-I", os.path.join(ROOT, "cpic_b200", "csrc", "host"), "-o", exe, src],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "bad=0" in r.stdout, r.stdout[-500:]
