@@ -90,6 +90,7 @@ EXPORTS = {
     "cpic_b200_image_bytes": (_i64, [_vp]),
     "cpic_b200_image_download": (_i, [_vp, _vp, _i64]),
     "cpic_b200_image_upload": (_i, [_vp, _vp, _i64]),
+    "cpic_b200_step_host": (_i, [_vp, _vp, _i64]),
     "cpic_b200_host_alloc": (_vp, [C.c_size_t]),
     "cpic_b200_host_free": (None, [_vp]),
     "cpic_b200_conf_load": (_i, [C.c_char_p, _pp]),
@@ -102,6 +103,10 @@ EXPORTS = {
     "cpic_b200_init_reference": (_i, [_vp, _i, _vp, _i64]),
     "cpic_b200_conf_stream_particles": (_i, [_vp, _i, _i64, _vp, _vp]),
     "cpic_b200_write_fields": (_i, [_vp, C.c_char_p, _i64, _i64, _i64, _i64, _d, _d]),
+    "cpic_b200_write_fields_async": (_i, [_vp, C.c_char_p, _i64, _i64, _i64, _i64, _i64, _d, _d]),
+    "cpic_b200_output_wait": (_i, [_vp]),
+    "cpic_b200_get_fields_begin": (_i, [_vp, _vp]),
+    "cpic_b200_get_fields_end": (_i, [_vp]),
     "cpic_b200_main": (_i, [_i, C.POINTER(C.c_char_p)]),
 }
 

@@ -3,7 +3,9 @@
  * field output layout (src/output.c:401-635), over the C ABI. Nothing here is on the
  * per-timestep path except the call to cpic_b200_step. */
 #include <errno.h>
+#include <fcntl.h>
 #include <math.h>
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -11,6 +13,7 @@
 #include <time.h>
 #include <unistd.h>
 
+#include <map>
 #include <string>
 #include <vector>
 
@@ -28,29 +31,78 @@ mkdir_ok(const std::string &p)
 	return 0;
 }
 
-/* write_field, reference src/output.c:482-590: the padded array as it is, rounded up to
- * whole `alignment` blocks (the reference's allocation pads with 0xca, src/mat.c:116) */
+/* One output in flight per simulation: pinned staging buffers for the four grids (whole `alignment`
+ * blocks, padded with 0xca as the reference's allocation is, src/mat.c:116) and the thread that writes
+ * them */
+struct OutCtx {
+	cpic_b200_sim_t *sim;
+	double *buf[4];
+	size_t total[4];
+	int64_t rows[4], stride[4];
+	pthread_t th;
+	bool running;
+	int status;
+	char err[512];
+	/* the job of the thread */
+	std::string root;
+	int64_t iter, alignment, slices, nx, ny;
+	double dx, dy;
+};
+
+static std::map<cpic_b200_sim_t *, OutCtx *> g_out;
+static pthread_mutex_t g_out_lock = PTHREAD_MUTEX_INITIALIZER;
+
+/* write_field, reference src/output.c:482-590: the padded array as it is, in `slices` runs of whole
+ * `alignment` blocks, O_DIRECT | O_SYNC like the reference (a file system that refuses O_DIRECT gets a
+ * plain write) */
 static int
-write_field(cpic_b200_sim_t *sim, int field, const std::string &file, int64_t alignment,
-		int64_t *rows_out, int64_t *stride_out)
+write_slices(const std::string &file, const unsigned char *data, size_t total, int64_t alignment, int64_t slices, char *err, size_t errlen)
 {
-	int64_t rows, stride;
-	if(cpic_b200_field_shape(sim, field, &rows, &stride)) return -1;
-	const size_t bytes = (size_t) rows * stride * sizeof(double);
-	const size_t total = (bytes + alignment - 1) / alignment * alignment;
-	std::vector<unsigned char> buf(total, 0xca);
-	if(cpic_b200_get_field(sim, field, (double *) buf.data())) return -1;
-	FILE *f = fopen(file.c_str(), "wb");
-	if(!f || fwrite(buf.data(), 1, total, f) != total)
+	int fd = open(file.c_str(), O_WRONLY | O_CREAT | O_TRUNC | O_DIRECT, S_IRUSR | S_IWUSR);
+	if(fd < 0) fd = open(file.c_str(), O_WRONLY | O_CREAT | O_TRUNC, S_IRUSR | S_IWUSR);
+	if(fd < 0) { snprintf(err, errlen, "cannot write %s: %s", file.c_str(), strerror(errno)); return -1; }
+	if(slices < 1) slices = 1;
+	const size_t blocks = total / (size_t) alignment;
+	const size_t per = blocks / (size_t) slices;
+	size_t left = blocks % (size_t) slices, offset = 0;
+	for(int64_t i = 0; i < slices; i++)
 	{
-		front_set_error("cannot write %s: %s", file.c_str(), strerror(errno));
-		if(f) fclose(f);
-		return -1;
+		size_t n = per * (size_t) alignment;
+		if(left > 0) { n += (size_t) alignment; left--; }
+		size_t done = 0;
+		while(done < n)
+		{
+			const ssize_t w = pwrite(fd, data + offset + done, n - done, (off_t) (offset + done));
+			if(w < 0 && errno == EINVAL)
+			{
+				/* O_DIRECT refused for this buffer or file system: write the rest the plain way */
+				const int fl = fcntl(fd, F_GETFL);
+				if(fl >= 0 && (fl & O_DIRECT) && fcntl(fd, F_SETFL, fl & ~O_DIRECT) == 0) continue;
+			}
+			if(w <= 0) { snprintf(err, errlen, "cannot write %s: %s", file.c_str(), strerror(errno)); close(fd); return -1; }
+			done += (size_t) w;
+		}
+		offset += n;
 	}
-	fclose(f);
-	*rows_out = rows;
-	*stride_out = stride;
+	close(fd);
 	return 0;
+}
+
+static int write_xdmf(const OutCtx &o);
+
+static void *
+out_thread(void *arg)
+{
+	OutCtx *o = (OutCtx *) arg;
+	o->status = 0;
+	if(cpic_b200_get_fields_end(o->sim)) { snprintf(o->err, sizeof(o->err), "%s", cpic_b200_last_error()); o->status = CPIC_B200_ECUDA; return NULL; }
+	const std::string dir = o->root + "/bin/" + std::to_string(o->iter);
+	const char *names[4] = { "rho", "phi", "E_X", "E_Y" };
+	for(int k = 0; k < 4 && !o->status; k++)
+		if(write_slices(dir + "/" + names[k] + ".bin", (const unsigned char *) o->buf[k], o->total[k], o->alignment, o->slices, o->err, sizeof(o->err)))
+			o->status = CPIC_B200_EINVAL;
+	if(!o->status && write_xdmf(*o)) o->status = CPIC_B200_EINVAL;
+	return NULL;
 }
 
 /* write_field_attribute, reference src/output.c:401-421 */
@@ -71,51 +123,111 @@ xdmf_attribute(FILE *f, long iter, const char *name, long nx, long ny, long dy, 
 	fprintf(f, "      </Attribute>\n");
 }
 
-/* output_fields, reference src/output.c:594-635 and write_xdmf_fields :423-460 */
-extern "C" int
-cpic_b200_write_fields(cpic_b200_sim_t *sim, const char *path, int64_t iter, int64_t alignment,
-		int64_t nx, int64_t ny, double dx, double dy)
+/* write_xdmf_fields, reference src/output.c:423-460 */
+static int
+write_xdmf(const OutCtx &o)
 {
-	if(!sim || !path) { front_set_error("null argument"); return CPIC_B200_EINVAL; }
-	if(alignment <= 0) alignment = 512;
-	const std::string root(path);
-	if(mkdir_ok(root) || mkdir_ok(root + "/xdmf") || mkdir_ok(root + "/bin")) return CPIC_B200_EINVAL;
-	const std::string dir = root + "/bin/" + std::to_string(iter);
-	if(mkdir_ok(dir)) return CPIC_B200_EINVAL;
-
-	int64_t rows[4], stride[4];
-	const char *names[4] = { "rho", "phi", "E_X", "E_Y" };
-	const int fields[4] = { CPIC_B200_RHO, CPIC_B200_PHI, CPIC_B200_EX, CPIC_B200_EY };
-	for(int k = 0; k < 4; k++)
-		if(write_field(sim, fields[k], dir + "/" + names[k] + ".bin", alignment, &rows[k], &stride[k]))
-			return CPIC_B200_EINVAL;
-
-	const std::string xf = root + "/xdmf/fields-iter" + std::to_string(iter) + ".xdmf";
+	const std::string xf = o.root + "/xdmf/fields-iter" + std::to_string(o.iter) + ".xdmf";
 	FILE *f = fopen(xf.c_str(), "w");
-	if(!f) { front_set_error("cannot write %s", xf.c_str()); return CPIC_B200_EINVAL; }
+	if(!f) return -1;
+	const int64_t *rows = o.rows, *stride = o.stride;
+	const long nx = (long) o.nx, ny = (long) o.ny;
 	fprintf(f, "<?xml version=\"1.0\" encoding=\"utf-8\"?>\n");
 	fprintf(f, "<Xdmf xmlns:xi=\"http://www.w3.org/2001/XInclude\" Version=\"3.0\">\n");
 	fprintf(f, "  <Domain>\n");
 	fprintf(f, "    <Grid Name=\"fields\">\n");
-	fprintf(f, "      <Topology TopologyType=\"3DCoRectMesh\" NumberOfElements=\"%ld %ld %ld\"/>\n", 1L, (long) ny, (long) nx);
+	fprintf(f, "      <Topology TopologyType=\"3DCoRectMesh\" NumberOfElements=\"%ld %ld %ld\"/>\n", 1L, ny, nx);
 	fprintf(f, "      <Geometry Origin=\"\" Type=\"ORIGIN_DXDYDZ\">\n");
 	fprintf(f, "        <DataItem Format=\"XML\" Dimensions=\"3\">\n");
 	fprintf(f, "            0.0 0.0 0.0\n");
 	fprintf(f, "        </DataItem>\n");
 	fprintf(f, "        <DataItem Format=\"XML\" Dimensions=\"3\">\n");
-	fprintf(f, "            %f %f %f\n", 0.0, dy, dx);
+	fprintf(f, "            %f %f %f\n", 0.0, o.dy, o.dx);
 	fprintf(f, "        </DataItem>\n");
 	fprintf(f, "      </Geometry>\n");
 	/* phi is a view one row into `_phi` (PHI_NG_NORTH, reference src/def.h:11, src/field.c:96) */
-	xdmf_attribute(f, (long) iter, "phi", (long) nx, (long) ny, 1, (long) rows[1], (long) stride[1]);
-	xdmf_attribute(f, (long) iter, "rho", (long) nx, (long) ny, 0, (long) rows[0], (long) stride[0]);
-	xdmf_attribute(f, (long) iter, "E_X", (long) nx, (long) ny, 0, (long) rows[2], (long) stride[2]);
-	xdmf_attribute(f, (long) iter, "E_Y", (long) nx, (long) ny, 0, (long) rows[3], (long) stride[3]);
+	xdmf_attribute(f, (long) o.iter, "phi", nx, ny, 1, (long) rows[1], (long) stride[1]);
+	xdmf_attribute(f, (long) o.iter, "rho", nx, ny, 0, (long) rows[0], (long) stride[0]);
+	xdmf_attribute(f, (long) o.iter, "E_X", nx, ny, 0, (long) rows[2], (long) stride[2]);
+	xdmf_attribute(f, (long) o.iter, "E_Y", nx, ny, 0, (long) rows[3], (long) stride[3]);
 	fprintf(f, "    </Grid>\n");
 	fprintf(f, "  </Domain>\n");
 	fprintf(f, "</Xdmf>\n");
 	fclose(f);
 	return 0;
+}
+
+static OutCtx *
+out_ctx(cpic_b200_sim_t *sim)
+{
+	pthread_mutex_lock(&g_out_lock);
+	OutCtx *&o = g_out[sim];
+	if(!o) { o = new OutCtx(); o->sim = sim; o->running = false; o->status = 0; for(int k = 0; k < 4; k++) { o->buf[k] = NULL; o->total[k] = 0; } }
+	OutCtx *r = o;
+	pthread_mutex_unlock(&g_out_lock);
+	return r;
+}
+
+extern "C" int
+cpic_b200_output_wait(cpic_b200_sim_t *sim)
+{
+	if(!sim) { front_set_error("null argument"); return CPIC_B200_EINVAL; }
+	OutCtx *o = out_ctx(sim);
+	if(!o->running) return 0;
+	pthread_join(o->th, NULL);
+	o->running = false;
+	if(o->status) front_set_error("%s", o->err);
+	return o->status;
+}
+
+/* output_fields, reference src/output.c:594-635: the grids start their way to pinned staging on a copy
+ * stream, a thread writes them (aligned slices, write_field src/output.c:482-590) and the XDMF descriptor */
+extern "C" int
+cpic_b200_write_fields_async(cpic_b200_sim_t *sim, const char *path, int64_t iter, int64_t alignment,
+		int64_t slices, int64_t nx, int64_t ny, double dx, double dy)
+{
+	if(!sim || !path) { front_set_error("null argument"); return CPIC_B200_EINVAL; }
+	if(alignment <= 0) alignment = 512;
+	int rc = cpic_b200_output_wait(sim);        /* the staging buffers are free again */
+	if(rc) return rc;
+	OutCtx *o = out_ctx(sim);
+	o->root = path;
+	if(mkdir_ok(o->root) || mkdir_ok(o->root + "/xdmf") || mkdir_ok(o->root + "/bin")
+			|| mkdir_ok(o->root + "/bin/" + std::to_string(iter))) return CPIC_B200_EINVAL;
+	const int fields[4] = { CPIC_B200_RHO, CPIC_B200_PHI, CPIC_B200_EX, CPIC_B200_EY };
+	for(int k = 0; k < 4; k++)
+	{
+		if(cpic_b200_field_shape(sim, fields[k], &o->rows[k], &o->stride[k])) return CPIC_B200_EINVAL;
+		const size_t bytes = (size_t) o->rows[k] * o->stride[k] * sizeof(double);
+		const size_t total = (bytes + alignment - 1) / alignment * alignment;
+		if(total != o->total[k])
+		{
+			cpic_b200_host_free(o->buf[k]);
+			o->buf[k] = (double *) cpic_b200_host_alloc(total);
+			if(!o->buf[k]) { o->total[k] = 0; front_set_error("pinned staging of %zu bytes failed", total); return CPIC_B200_ENOMEM; }
+			o->total[k] = total;
+		}
+		memset((unsigned char *) o->buf[k] + bytes, 0xca, total - bytes);
+	}
+	if(cpic_b200_get_fields_begin(sim, o->buf)) return CPIC_B200_ECUDA;
+	o->iter = iter; o->alignment = alignment; o->slices = slices; o->nx = nx; o->ny = ny; o->dx = dx; o->dy = dy;
+	if(pthread_create(&o->th, NULL, out_thread, o))
+	{
+		out_thread(o);          /* no thread: write here */
+		if(o->status) front_set_error("%s", o->err);
+		return o->status;
+	}
+	o->running = true;
+	return 0;
+}
+
+extern "C" int
+cpic_b200_write_fields(cpic_b200_sim_t *sim, const char *path, int64_t iter, int64_t alignment,
+		int64_t nx, int64_t ny, double dx, double dy)
+{
+	int rc = cpic_b200_write_fields_async(sim, path, iter, alignment, 1, nx, ny, dx, dy);
+	if(rc) return rc;
+	return cpic_b200_output_wait(sim);
 }
 
 static double
@@ -185,7 +297,7 @@ cpic_b200_main(int argc, char **argv)
 		if(run.output_enabled)
 		{
 			if(cpic_b200_stage_field_E(sim)
-					|| cpic_b200_write_fields(sim, run.output_path, cpic_b200_iter(sim), run.output_alignment, p.nx, p.ny, dx, dy)
+					|| cpic_b200_write_fields_async(sim, run.output_path, cpic_b200_iter(sim), run.output_alignment, run.output_slices, p.nx, p.ny, dx, dy)
 					|| cpic_b200_stage_plasma_E(sim) || cpic_b200_stage_plasma_r(sim) || cpic_b200_stage_field_rho(sim)
 					|| cpic_b200_set_iter(sim, cpic_b200_iter(sim) + 1))
 			{
@@ -224,6 +336,11 @@ cpic_b200_main(int argc, char **argv)
 				running = 0;
 			}
 		}
+	}
+	if(cpic_b200_output_wait(sim))
+	{
+		fprintf(stderr, "output failed\n%s\n", cpic_b200_last_error());
+		return 1;
 	}
 	printf("Simulation ends\n");
 	cpic_b200_destroy(sim);

@@ -1337,6 +1337,30 @@ k_image_copy(SpeciesDev sp, int nb, const int *__restrict__ cnt, const long long
 	if(pack <= 0 && lane == 0) sp.count[b] = at + c;
 }
 
+/* Exclusive prefix of the block counts (the offsets of the compact image), by one CTA: every thread
+ * sums a contiguous share, the shares are scanned in shared memory, then written out. */
+static __global__ void __launch_bounds__(1024)
+k_count_offsets(const int *__restrict__ cnt, int nb, long long *__restrict__ off)
+{
+	__shared__ long long part[1024];
+	const int per = (nb + 1023) / 1024;
+	const int b0 = threadIdx.x * per, b1 = min(nb, b0 + per);
+	long long sum = 0;
+	for(int b = b0; b < b1; b++) sum += cnt[b];
+	part[threadIdx.x] = sum;
+	__syncthreads();
+	for(int o = 1; o < 1024; o <<= 1)
+	{
+		const long long v = (int) threadIdx.x >= o ? part[threadIdx.x - o] : 0;
+		__syncthreads();
+		part[threadIdx.x] += v;
+		__syncthreads();
+	}
+	long long run = part[threadIdx.x] - sum;
+	for(int b = b0; b < b1; b++) { off[b] = run; run += cnt[b]; }
+	if(threadIdx.x == 1023) off[nb] = part[1023];
+}
+
 /* Particles in the HOST's order (the drop-in binding keeps the reference's lists, which never
  * reorder): pos[id] is the place of particle `id` in the host's walk over its lists; entry
  * pos[id] of each of the seven output arrays (x y ux uy uz E_x E_y, n values each) receives the

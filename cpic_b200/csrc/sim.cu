@@ -86,6 +86,15 @@ struct cpic_b200_sim {
 	double umax[3];
 	cudaStream_t stream;
 	cudaStream_t stream2;    /* pushes of the odd species (forked from / joined into `stream`) */
+	cudaStream_t stream_fields;              /* cpic_b200_get_fields_begin: grid downloads next to the compute stream */
+	cudaEvent_t ev_fields_from, ev_fields_done;
+	bool fields_pending;
+	cudaStream_t stream_in, stream_out;      /* cpic_b200_step_host: uploads / downloads next to the compute stream */
+	cudaEvent_t ev_up[CPIC_B200_MAX_SPECIES], ev_packed[CPIC_B200_MAX_SPECIES];
+	double *hstage[2][CPIC_B200_MAX_SPECIES];        /* device staging of the species' images: [up / down] */
+	size_t hstage_cap[2][CPIC_B200_MAX_SPECIES];
+	long long *hoff[2][CPIC_B200_MAX_SPECIES];       /* block offsets of those images (nb + 1) */
+	int *hcnt[CPIC_B200_MAX_SPECIES];                /* uploaded block counts */
 	cudaEvent_t ev_fork, ev_join;
 	bool overlap_species;
 	int device;
@@ -398,6 +407,18 @@ cpic_b200_destroy(cpic_b200_sim_t *s)
 	if(s->ev[1]) cudaEventDestroy(s->ev[1]);
 	if(s->stream) cudaStreamDestroy(s->stream);
 	if(s->stream2) cudaStreamDestroy(s->stream2);
+	if(s->stream_fields) { cudaStreamSynchronize(s->stream_fields); cudaStreamDestroy(s->stream_fields); }
+	if(s->ev_fields_from) cudaEventDestroy(s->ev_fields_from);
+	if(s->ev_fields_done) cudaEventDestroy(s->ev_fields_done);
+	if(s->stream_in) cudaStreamDestroy(s->stream_in);
+	if(s->stream_out) cudaStreamDestroy(s->stream_out);
+	for(int i = 0; i < CPIC_B200_MAX_SPECIES; i++)
+	{
+		if(s->ev_up[i]) cudaEventDestroy(s->ev_up[i]);
+		if(s->ev_packed[i]) cudaEventDestroy(s->ev_packed[i]);
+		for(int k = 0; k < 2; k++) { cudaFree(s->hstage[k][i]); cudaFree(s->hoff[k][i]); }
+		cudaFree(s->hcnt[i]);
+	}
 	if(s->ev_fork) cudaEventDestroy(s->ev_fork);
 	if(s->ev_join) cudaEventDestroy(s->ev_join);
 	delete s;
@@ -427,6 +448,7 @@ in_slab_rows(const Geom &g, double y)
 static int ensure_particle_E(sim_t_ *s, int is);
 static int image_staging(sim_t_ *s, size_t doubles);
 static int p2p_attach(sim_t_ *s);
+static int fields_guard(sim_t_ *s);
 
 static int alloc_species_storage(sim_t_ *s, int is, int cap);
 
@@ -1344,6 +1366,7 @@ cpic_b200_stage_field_E(cpic_b200_sim_t *s)
 	CK(cudaSetDevice(s->device));
 	const Geom &g = s->g;
 	int rc;
+	if((rc = fields_guard(s))) return rc;
 	{
 		StageTimer ts(s, T_SOLVER);
 		rc = solve(s);
@@ -1507,6 +1530,7 @@ cpic_b200_stage_field_rho(cpic_b200_sim_t *s)
 	if(!s) return fail(CPIC_B200_EINVAL, "null sim");
 	if(s->p.nranks > 1 && !s->comm) return fail(CPIC_B200_EINVAL, "rank %d of %d has no communicator: call cpic_b200_comm_init first", s->p.rank, s->p.nranks);
 	CK(cudaSetDevice(s->device));
+	{ int rc = fields_guard(s); if(rc) return rc; }
 	StageTimer t(s, T_RHO);
 	const Geom &g = s->g;
 	static_assert(DEP_MAX_SPECIES >= CPIC_B200_MAX_SPECIES, "deposit set too small");
@@ -1714,6 +1738,58 @@ cpic_b200_get_field(cpic_b200_sim_t *s, int f, double *host)
 	return 0;
 }
 
+/* output_fields without stalling the step (reference src/output.c:594-635 writes the grids right
+ * after stage_field_E, src/sim.c:507): the four arrays start their way to (pinned) host buffers on a
+ * copy stream of their own, behind everything issued so far; the stages that overwrite a grid
+ * (stage_field_rho: rho, the next stage_field_E: phi and E) wait for the copy on the device, the host
+ * does not wait until cpic_b200_get_fields_end. host[f] == NULL skips grid f. */
+extern "C" int
+cpic_b200_get_fields_begin(cpic_b200_sim_t *s, double *const host[4])
+{
+	if(!s || !host) return fail(CPIC_B200_EINVAL, "null argument");
+	CK(cudaSetDevice(s->device));
+	if(!s->stream_fields)
+	{
+		CK(cudaStreamCreateWithFlags(&s->stream_fields, cudaStreamNonBlocking));
+		CK(cudaEventCreateWithFlags(&s->ev_fields_from, cudaEventDisableTiming));
+		CK(cudaEventCreateWithFlags(&s->ev_fields_done, cudaEventDisableTiming));
+	}
+	CK(cudaEventRecord(s->ev_fields_from, s->stream));
+	CK(cudaStreamWaitEvent(s->stream_fields, s->ev_fields_from, 0));
+	for(int f = 0; f < 4; f++)
+	{
+		if(!host[f]) continue;
+		double *base = NULL; int64_t r = 0, st = 0, ds = 0;
+		int rc = field_geom(s, f, &base, &r, &st, &ds);
+		if(rc) return rc;
+		CK(cudaMemcpy2DAsync(host[f], (size_t) st * sizeof(double), base, (size_t) ds * sizeof(double),
+					(size_t) st * sizeof(double), (size_t) r, cudaMemcpyDeviceToHost, s->stream_fields));
+	}
+	CK(cudaEventRecord(s->ev_fields_done, s->stream_fields));
+	s->fields_pending = true;
+	return 0;
+}
+
+extern "C" int
+cpic_b200_get_fields_end(cpic_b200_sim_t *s)
+{
+	if(!s) return fail(CPIC_B200_EINVAL, "null sim");
+	if(!s->stream_fields) return 0;
+	CK(cudaSetDevice(s->device));
+	CK(cudaEventSynchronize(s->ev_fields_done));
+	return 0;
+}
+
+/* the grids are about to be overwritten: a download in flight goes first (on the device) */
+static int
+fields_guard(sim_t_ *s)
+{
+	if(!s->fields_pending) return 0;
+	CK(cudaStreamWaitEvent(s->stream, s->ev_fields_done, 0));
+	s->fields_pending = false;
+	return 0;
+}
+
 extern "C" int
 cpic_b200_set_field(cpic_b200_sim_t *s, int f, const double *host)
 {
@@ -1875,6 +1951,115 @@ cpic_b200_image_upload(cpic_b200_sim_t *s, const void *host, int64_t bytes)
 		p += 6 * 8 * n;
 	}
 	return 0;
+}
+
+/* One sim_step with the particle state living in pinned HOST memory (the image of
+ * cpic_b200_image_download): every species is uploaded, pushed and downloaded in turn on three
+ * streams, so that the upload of one species runs while the previous one is pushed and downloaded
+ * -- PCIe is full duplex, the serial upload / step / download uses one direction at a time. The
+ * image comes back with the new block counts and particles. One rank (the population of a rank
+ * changes with several); the capacities must hold the step (no growth in flight). */
+extern "C" int
+cpic_b200_step_host(cpic_b200_sim_t *s, void *host, int64_t bytes)
+{
+	if(!s || !host) return fail(CPIC_B200_EINVAL, "null argument");
+	if(s->iter < 0) return fail(CPIC_B200_EINVAL, "call cpic_b200_pre_step first");
+	if(s->comm) return fail(CPIC_B200_EINVAL, "cpic_b200_step_host runs on one rank");
+	CK(cudaSetDevice(s->device));
+	if(!s->stream_in)
+	{
+		CK(cudaStreamCreateWithFlags(&s->stream_in, cudaStreamNonBlocking));
+		CK(cudaStreamCreateWithFlags(&s->stream_out, cudaStreamNonBlocking));
+		for(int i = 0; i < CPIC_B200_MAX_SPECIES; i++)
+		{
+			CK(cudaEventCreateWithFlags(&s->ev_up[i], cudaEventDisableTiming));
+			CK(cudaEventCreateWithFlags(&s->ev_packed[i], cudaEventDisableTiming));
+		}
+	}
+	char *p = (char *) host, *end = p + bytes;
+	const size_t cbytes = ((size_t) s->nb * 4 + 7) & ~(size_t) 7;
+	struct Sub { long long n; int *cnt; double *data; } sub[CPIC_B200_MAX_SPECIES];
+	std::vector<long long> off[CPIC_B200_MAX_SPECIES];
+	/* whatever ran before (a download that filled the image) is complete */
+	CK(cudaStreamSynchronize(s->stream));
+	for(int is = 0; is < s->p.nspecies; is++)
+	{
+		SpeciesHost &h = s->sp[is];
+		sub[is].n = -1;
+		if(!h.block) continue;
+		if(p + 8 > end) return fail(CPIC_B200_EINVAL, "truncated image");
+		Sub &u = sub[is];
+		u.n = *(const int64_t *) p; p += 8;
+		u.cnt = (int *) p; p += cbytes;
+		u.data = (double *) p;
+		if(u.n < 0 || p + 6 * 8 * u.n > end) return fail(CPIC_B200_EINVAL, "truncated image");
+		p += 6 * 8 * u.n;
+		off[is].resize((size_t) s->nb + 1);
+		long long m = 0;
+		for(int b = 0; b < s->nb; b++)
+		{
+			if(u.cnt[b] < 0 || u.cnt[b] > h.d.cap) return fail(CPIC_B200_ECAPACITY, "image block %d holds %d particles, capacity %d", b, u.cnt[b], h.d.cap);
+			off[is][(size_t) b] = m; m += u.cnt[b];
+		}
+		off[is][(size_t) s->nb] = m;
+		if(m != u.n) return fail(CPIC_B200_EINVAL, "image counts do not add up");
+		for(int k = 0; k < 2; k++)
+		{
+			if(s->hstage_cap[k][is] < (size_t) 6 * (size_t) u.n)
+			{
+				cudaFree(s->hstage[k][is]);
+				s->hstage[k][is] = NULL; s->hstage_cap[k][is] = 0;
+				CK(cudaMalloc(&s->hstage[k][is], (size_t) 6 * (size_t) u.n * sizeof(double)));
+				s->hstage_cap[k][is] = (size_t) 6 * (size_t) u.n;
+			}
+			if(!s->hoff[k][is]) CK(cudaMalloc(&s->hoff[k][is], ((size_t) s->nb + 1) * sizeof(long long)));
+		}
+		if(!s->hcnt[is]) CK(cudaMalloc(&s->hcnt[is], (size_t) s->nb * sizeof(int)));
+		/* upload: counts, offsets, the six arrays */
+		CK(cudaMemcpyAsync(s->hcnt[is], u.cnt, (size_t) s->nb * sizeof(int), cudaMemcpyHostToDevice, s->stream_in));
+		CK(cudaMemcpyAsync(s->hoff[0][is], off[is].data(), ((size_t) s->nb + 1) * sizeof(long long), cudaMemcpyHostToDevice, s->stream_in));
+		CK(cudaMemcpyAsync(s->hstage[0][is], u.data, (size_t) 6 * (size_t) u.n * sizeof(double), cudaMemcpyHostToDevice, s->stream_in));
+		CK(cudaEventRecord(s->ev_up[is], s->stream_in));
+	}
+	/* the fields of this step do not depend on the upload */
+	int rc = cpic_b200_stage_field_E(s);
+	if(rc) return rc;
+	int *flag = s->errflag + 15;
+	CK(cudaMemsetAsync(flag, 0, sizeof(int), s->stream));
+	for(int is = 0; is < s->p.nspecies; is++)
+	{
+		SpeciesHost &h = s->sp[is];
+		const Sub &u = sub[is];
+		if(u.n < 0) continue;
+		CK(cudaStreamWaitEvent(s->stream, s->ev_up[is], 0));
+		/* the image holds every particle: no arrivals are pending afterwards */
+		for(int k = 0; k < 2; k++) CK(cudaMemsetAsync(h.d.ob[k].count, 0, (size_t) s->nob * 9 * sizeof(int), s->stream));
+		k_image_copy<<<(s->nb + 7) / 8, 256, 0, s->stream>>>(h.d, s->nb, s->hcnt[is], s->hoff[0][is], s->hstage[0][is], u.n, 0);
+		if((rc = check_launch(s))) return rc;
+		if((rc = launch_gather_push<2>(s, is, s->stream))) return rc;
+		SpeciesSet set;
+		set.sp[0] = h.d; set.arr[0] = h.arr; set.n = 1;
+		k_far_insert<<<1, 1024, 0, s->stream>>>(set, s->g, s->errflag);
+		k_absorb<<<(s->nb + 7) / 8, 256, 0, s->stream>>>(h.d, s->g, s->nb, h.arr, flag);
+		k_count_offsets<<<1, 1024, 0, s->stream>>>(h.d.count, s->nb, s->hoff[1][is]);
+		k_image_copy<<<(s->nb + 7) / 8, 256, 0, s->stream>>>(h.d, s->nb, h.d.count, s->hoff[1][is], s->hstage[1][is], u.n, 1);
+		if((rc = check_launch(s, 4))) return rc;
+		CK(cudaEventRecord(s->ev_packed[is], s->stream));
+		CK(cudaStreamWaitEvent(s->stream_out, s->ev_packed[is], 0));
+		CK(cudaMemcpyAsync(u.cnt, h.d.count, (size_t) s->nb * sizeof(int), cudaMemcpyDeviceToHost, s->stream_out));
+		CK(cudaMemcpyAsync(u.data, s->hstage[1][is], (size_t) 6 * (size_t) u.n * sizeof(double), cudaMemcpyDeviceToHost, s->stream_out));
+	}
+	rc = cpic_b200_stage_field_rho(s);
+	if(rc) return rc;
+	s->iter++;
+	CK(cudaMemcpyAsync(s->h_err + 15, flag, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+	CK(cudaStreamSynchronize(s->stream_in));
+	CK(cudaStreamSynchronize(s->stream_out));
+	CK(cudaStreamSynchronize(s->stream));
+	if(s->h_err[15])
+		return fail(CPIC_B200_ECAPACITY, "a particle block could not take its arrivals during cpic_b200_step_host: "
+				"raise capacity_factor (now %g)", s->p.capacity_factor);
+	return cpic_b200_sync(s);
 }
 
 extern "C" void *

@@ -179,6 +179,11 @@ int cpic_b200_field_shape(cpic_b200_sim_t *sim, int field, int64_t *rows, int64_
  * src/output.c:627-630). `host` holds rows*stride doubles. */
 int cpic_b200_get_field(cpic_b200_sim_t *sim, int field, double *host);
 int cpic_b200_set_field(cpic_b200_sim_t *sim, int field, const double *host);
+/* The four grids on their way to host buffers (pinned: cpic_b200_host_alloc) without stalling the step:
+ * the copies run on a stream of their own behind the work issued so far; stages that overwrite a grid
+ * wait for them on the device. host[field] == NULL skips a grid. cpic_b200_get_fields_end waits. */
+int cpic_b200_get_fields_begin(cpic_b200_sim_t *sim, double *const host[4]);
+int cpic_b200_get_fields_end(cpic_b200_sim_t *sim);
 
 /* Solver seam (src/solver.h:46-59): phi slab rows <- solve(rho slab rows); no ghosts */
 int cpic_b200_solve(cpic_b200_sim_t *sim);
@@ -202,6 +207,11 @@ int cpic_b200_get_timing(cpic_b200_sim_t *sim, double ms[6], int64_t launches[1]
 int64_t cpic_b200_image_bytes(cpic_b200_sim_t *sim);
 int cpic_b200_image_download(cpic_b200_sim_t *sim, void *host, int64_t bytes);
 int cpic_b200_image_upload(cpic_b200_sim_t *sim, const void *host, int64_t bytes);
+/* One sim_step with the particle state living in pinned host memory: `host` is an image as written by
+ * cpic_b200_image_download; every species is uploaded, pushed and downloaded in turn on three streams
+ * (the upload of one species overlaps the push and the download of the previous one: PCIe runs in both
+ * directions at once); the image comes back with the new block counts and particles. One rank. */
+int cpic_b200_step_host(cpic_b200_sim_t *sim, void *host, int64_t bytes);
 void *cpic_b200_host_alloc(size_t bytes);   /* pinned */
 void cpic_b200_host_free(void *p);
 
@@ -264,6 +274,13 @@ int cpic_b200_sim_from_conf(const char *path, int rank, int nranks, int device, 
  * <path>/xdmf/fields-iter<iter>.xdmf with the reference's hyperslab descriptors. */
 int cpic_b200_write_fields(cpic_b200_sim_t *sim, const char *path, int64_t iter, int64_t alignment,
 		int64_t nx, int64_t ny, double dx, double dy);
+/* The same without waiting: the grids are copied to pinned staging buffers on a copy stream and written by
+ * a background thread -- aligned slices with O_DIRECT as the reference does (src/output.c:482-590; `slices`
+ * = output.slices) -- while the step goes on. One output in flight per simulation: the next call, or
+ * cpic_b200_output_wait, waits for the previous one and returns its status. */
+int cpic_b200_write_fields_async(cpic_b200_sim_t *sim, const char *path, int64_t iter, int64_t alignment,
+		int64_t slices, int64_t nx, int64_t ny, double dx, double dy);
+int cpic_b200_output_wait(cpic_b200_sim_t *sim);
 /* The reference's command line, `cpic [-q] <conf>` (src/cpic.c:50-191), on one GPU */
 int cpic_b200_main(int argc, char **argv);
 

@@ -254,3 +254,40 @@ def test_device_initialiser_draws_the_reference_initial_conditions(conf, nprocs)
         assert relerr(b.field(k), a.field(k)) <= 1e-13, (conf, k)
     a.close()
     b.close()
+
+
+def test_step_with_the_state_in_host_memory():
+    """cpic_b200_step_host (the e2e path of bench.py): upload, sim_step and download of the particle image
+    species by species on three streams give the state of a resident cpic_b200_step (the deposit groups
+    absorbed arrivals differently from pending ones: rounding-level differences in rho, hence 1e-12)."""
+    import ctypes as C
+    path = conf_path("2d-2species-small.conf")
+    a = Sim.from_conf(path)
+    b = Sim.from_conf(path)
+    L = b.L
+    nbytes = L.cpic_b200_image_bytes(b.h)
+    host = L.cpic_b200_host_alloc(nbytes)
+    assert host
+    try:
+        assert L.cpic_b200_image_download(b.h, host, nbytes) == 0
+        for it in range(6):
+            a.step()
+            rc = L.cpic_b200_step_host(b.h, host, nbytes)
+            assert rc == 0, L.cpic_b200_last_error()
+        a.sync()
+        assert b.iter == a.iter
+        for k in ("rho", "phi", "Ex", "Ey"):
+            assert relerr(b.raw_field(k)[:, :a.params.nx], a.raw_field(k)[:, :a.params.nx]) <= TOL, k
+        for i in range(a.nspecies):
+            pa, pb = a.particles(i), b.particles(i)
+            assert np.array_equal(pa["id"], pb["id"])
+            for k, scale in (("x", a.params.Lx), ("y", a.params.Ly), ("ux", np.abs(pa["ux"]).max()), ("uy", np.abs(pa["uy"]).max())):
+                assert np.abs(pa[k] - pb[k]).max() / max(scale, 1e-300) <= TOL, (i, k)
+        # and the image itself holds the same particles
+        img = (C.c_char * nbytes).from_address(host)
+        n0 = np.frombuffer(img, np.int64, 1, 0)[0]
+        assert n0 == a.num_particles(0)
+    finally:
+        L.cpic_b200_host_free(host)
+        a.close()
+        b.close()

@@ -164,3 +164,42 @@ def test_physics_under_the_interpreter(simt_build):
     """Two-stream growth rate and energy history, constant speed and cyclotron orbits (the 1200-step
     harmonic golden trajectory is left to the GPU run: minutes of interpretation)."""
     run_under_interpreter(simt_build, ["tests/test_gpu_physics.py", "-k", "two_stream or constant_speed or cyclotron"])
+
+
+def test_own_driver_and_asynchronous_output_under_the_interpreter(simt_build, tmp_path):
+    """cpic_b200_main (the stand-alone driver: cpic's command line and run loop) with output enabled, served by
+    the interpreted kernels: grids copied on the copy stream into pinned staging and written by the
+    background thread in aligned slices -- same file sizes, values (1e-12) and XDMF text as the CPU
+    reference's own output.c."""
+    import numpy as np
+    ref = os.path.join(ROOT, "oracle", "_ref", "cpic_ref")
+    if not os.path.exists(ref):
+        pytest.skip("cpic_ref not built (needs /root/reference at build time)")
+    text = open(os.path.join(ROOT, "conf", "two-streams.conf")).read().replace("cycles = 800", "cycles = 4")
+    outs = {}
+    for name in ("gpu", "cpu"):
+        d = tmp_path / name
+        conf = tmp_path / f"{name}.conf"
+        conf.write_text(text + f'\noutput = {{ path = "{d}" slices = 4 alignment = 4096 }}\n')
+        if name == "cpu":
+            r = subprocess.run([ref, "-q", str(conf)], cwd=ROOT, capture_output=True, text=True, timeout=300)
+        else:
+            code = ("import ctypes as C, sys; L = C.CDLL(sys.argv[1]); "
+                    "argv = (C.c_char_p * 3)(b'cpic', b'-q', sys.argv[2].encode()); sys.exit(L.cpic_b200_main(3, argv))")
+            r = subprocess.run([sys.executable, "-c", code, simt_build, str(conf)], cwd=ROOT, capture_output=True, text=True,
+                               timeout=600, env=dict(os.environ, CPIC_B200_SIMT_CHECK="1"))
+        assert r.returncode == 0, r.stderr[-2000:] + r.stdout[-500:]
+        outs[name] = d
+    nx = 64
+    for it in range(4):
+        for f in ("rho", "phi", "E_X", "E_Y"):
+            pa, pb = outs["gpu"] / "bin" / str(it) / f"{f}.bin", outs["cpu"] / "bin" / str(it) / f"{f}.bin"
+            assert os.path.getsize(pa) == os.path.getsize(pb) and os.path.getsize(pa) % 4096 == 0
+            a, b = np.fromfile(pa), np.fromfile(pb)
+            ok = np.isfinite(b) & (np.abs(b) < 1e300)
+            if f in ("rho", "phi"):
+                ok &= (np.arange(a.size) % (nx + 2)) < nx
+            n_live = {"rho": 65, "phi": 67, "E_X": 65, "E_Y": 65}[f] * (nx + 2 if f in ("rho", "phi") else nx)
+            ok &= np.arange(a.size) < n_live
+            assert np.abs(a[ok] - b[ok]).max() <= 1e-12 * np.abs(b[ok]).max(), (it, f)
+        assert (outs["gpu"] / "xdmf" / f"fields-iter{it}.xdmf").read_text() == (outs["cpu"] / "xdmf" / f"fields-iter{it}.xdmf").read_text()
