@@ -42,6 +42,14 @@
 #define SEG_AOSOA 0
 #endif
 
+/* SEG_TENSOR 1 (plain layout only): the fused kernel fetches a batch of the own segment -- 32 slots of
+ * x y ux uy uz (id) -- with ONE tensor copy (cp.async.bulk.tensor.2d over the species' storage seen as
+ * a 2D tensor slot x array) instead of five or six 1D bulk copies: the elected lane's issue sequence
+ * was a fifth of the kernel's instructions */
+#ifndef SEG_TENSOR
+#define SEG_TENSOR (!SEG_AOSOA)
+#endif
+
 /* doubles from a batch's x values to its y values (and so on): SEG_STEP = 32 batch-major;
  * in the plain layout the arrays are SpeciesDev::astride apart */
 #if SEG_AOSOA
@@ -526,6 +534,7 @@ template <int MODE>
 __global__ void __launch_bounds__(32 * MAX_WPC, PUSH_MIN_CTAS)
 k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 		const __grid_constant__ CUtensorMap mapEx, const __grid_constant__ CUtensorMap mapEy,
+		const __grid_constant__ CUtensorMap mapS5, const __grid_constant__ CUtensorMap mapS6,
 		int nb, int cur, int *__restrict__ errflag)
 {
 	constexpr int NARR = PipeArrays<MODE>::N;
@@ -604,7 +613,11 @@ k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 			const int na_ = (MODE == 0 ? 2 : 5) + ((MODE != 0 && (with_id)) ? 1 : 0) + (MODE == 1 ? 2 : 0); \
 			mbar_expect_tx(mb_, (uint32_t) na_ * 256u); \
 			const seg_index_t g_ = seg_slot(sp.cap, b, (bi) * 32); \
-			if(SEG_AOSOA) { \
+			if(SEG_TENSOR && MODE == 2) { \
+				/* the segment arrays as a 2D tensor (slot, array): the batch's five or six arrays are \
+				 * one box, one TMA instruction */ \
+				tma_load_2d(st0_, (with_id) ? &mapS6 : &mapS5, (int) g_, 0, mb_); \
+			} else if(SEG_AOSOA) { \
 				/* the batch's arrays are contiguous: one copy */ \
 				tma_bulk_load(st0_, sp.x + g_, (MODE == 0 ? 2u : (with_id) ? 6u : 5u) * 256u, mb_); \
 			} else { \
@@ -1219,39 +1232,56 @@ k_deposit(const __grid_constant__ DepositSet set, Geom g, int nb, int ncol_rt, d
 			const double *__restrict__ sy = sp.y + seg_slot(sp.cap, b, 0);
 #define SEG(i) (i)
 #endif
-			/* own segment: two particles per lane and turn, the next four already on their way */
-			int k = lane;
-			double xa = 0, ya = 0, xb = 0, yb = 0, xc = 0, yc = 0, xd = 0, yd = 0;
-			if(k < cnt) { xa = sx[SEG(k)]; ya = sy[SEG(k)]; }
-			if(k + 32 < cnt) { xb = sx[SEG(k + 32)]; yb = sy[SEG(k + 32)]; }
-			if(k + 64 < cnt) { xc = sx[SEG(k + 64)]; yc = sy[SEG(k + 64)]; }
-			if(k + 96 < cnt) { xd = sx[SEG(k + 96)]; yd = sy[SEG(k + 96)]; }
+			/* own segment: two particles per lane and turn; four such pairs per lane are kept in flight
+			 * in four register slots that are refilled right after use (no rotation: a slot's loads have
+			 * three turns to arrive) */
+			double px[4][2], py[4][2];
+#pragma unroll
+			for(int q = 0; q < 4; q++)
+#pragma unroll
+				for(int e = 0; e < 2; e++)
+				{
+					const int kk = lane + 64 * q + 32 * e;
+					px[q][e] = 0.0; py[q][e] = 0.0;
+					if(kk < cnt) { px[q][e] = sx[SEG(kk)]; py[q][e] = sy[SEG(kk)]; }
+				}
 			/* the arrival counters travel while the segment is walked */
 			__syncwarp();
 			const Arrivals A = find_arrivals(sp.acount, sp.nob, g, nb, b, lane, scratch);
-			for(; k - lane < cnt; k += 64)
+			for(int k0 = 0; k0 < cnt; k0 += 256)
 			{
-				double nx_ = 0, ny_ = 0, mx_ = 0, my_ = 0;
-				if(k + 128 < cnt) { nx_ = sx[SEG(k + 128)]; ny_ = sy[SEG(k + 128)]; }
-				if(k + 160 < cnt) { mx_ = sx[SEG(k + 160)]; my_ = sy[SEG(k + 160)]; }
-				const DepContribution ca = dep_contribution(g, xa, ya, vq, k < cnt, cx0, cy0, NW, ncol, col);
-				const DepContribution cb = dep_contribution(g, xb, yb, vq, k + 32 < cnt, cx0, cy0, NW, ncol, col);
-				DEP_TURN(dep_add(t, ca, ncol, rowstep); dep_add(t, cb, ncol, rowstep););
-				xa = xc; ya = yc; xb = xd; yb = yd;
-				xc = nx_; yc = ny_; xd = mx_; yd = my_;
+#pragma unroll
+				for(int q = 0; q < 4; q++)
+				{
+					const int k = k0 + 64 * q + lane;
+					if(k - lane >= cnt) break;           /* warp-uniform */
+					const DepContribution ca = dep_contribution(g, px[q][0], py[q][0], vq, k < cnt, cx0, cy0, NW, ncol, col);
+					const DepContribution cb = dep_contribution(g, px[q][1], py[q][1], vq, k + 32 < cnt, cx0, cy0, NW, ncol, col);
+#pragma unroll
+					for(int e = 0; e < 2; e++)
+					{
+						const int kk = k + 256 + 32 * e;
+						px[q][e] = 0.0; py[q][e] = 0.0;
+						if(kk < cnt) { px[q][e] = sx[SEG(kk)]; py[q][e] = sy[SEG(kk)]; }
+					}
+					DEP_TURN(dep_add(t, ca, ncol, rowstep); dep_add(t, cb, ncol, rowstep););
+				}
 			}
-			/* arrivals: (x, y) are the first 16 bytes of a 48-byte record */
-			int f = lane;
-			double2 v = make_double2(0.0, 0.0), v2 = make_double2(0.0, 0.0);
-			if(f < A.total) v = *(const double2 *) (sp.arec + (size_t) arrival_slot(A, sp.roff, sp.rcap, f) * OREC);
-			if(f + 32 < A.total) v2 = *(const double2 *) (sp.arec + (size_t) arrival_slot(A, sp.roff, sp.rcap, f + 32) * OREC);
-			for(; f - lane < A.total; f += 32)
+			/* arrivals: (x, y) are the first 16 bytes of a 48-byte record; two per lane and turn as well,
+			 * the next two on their way */
+			auto arrival = [&](int f) -> double2
 			{
-				double2 nv = make_double2(0.0, 0.0);
-				if(f + 64 < A.total) nv = *(const double2 *) (sp.arec + (size_t) arrival_slot(A, sp.roff, sp.rcap, f + 64) * OREC);
-				const DepContribution ca = dep_contribution(g, v.x, v.y, vq, f < A.total, cx0, cy0, NW, ncol, col);
-				DEP_TURN(dep_add(t, ca, ncol, rowstep););
-				v = v2; v2 = nv;
+				if(f >= A.total) return make_double2(0.0, 0.0);
+				return *(const double2 *) (sp.arec + (size_t) arrival_slot(A, sp.roff, sp.rcap, f) * OREC);
+			};
+			double2 va = arrival(lane), vb = arrival(lane + 32);
+			for(int f = lane; f - lane < A.total; f += 64)
+			{
+				const double2 na = arrival(f + 64), nb2 = arrival(f + 96);
+				const DepContribution ca = dep_contribution(g, va.x, va.y, vq, f < A.total, cx0, cy0, NW, ncol, col);
+				const DepContribution cb = dep_contribution(g, vb.x, vb.y, vq, f + 32 < A.total, cx0, cy0, NW, ncol, col);
+				DEP_TURN(dep_add(t, ca, ncol, rowstep); dep_add(t, cb, ncol, rowstep););
+				va = na; vb = nb2;
 			}
 		}
 #undef DEP_TURN

@@ -61,6 +61,7 @@ extern "C" const char *cpic_b200_version(void) { return "cpic_b200 0.1 (sm_100a)
 
 struct SpeciesHost {
 	SpeciesDev d;
+	CUtensorMap segmap[2];   /* the segment arrays as a 2D tensor (slot, array): boxes of 32 x 5 and 32 x 6 */
 	void *block;             /* one allocation: x y ux uy uz id count (the "image") */
 	size_t block_bytes;
 	void *oblock;            /* the two outboxes */
@@ -165,6 +166,33 @@ make_tensor_map(CUtensorMap *map, double *base, const Geom &g)
 	if(r != CUDA_SUCCESS)
 		return fail(CPIC_B200_ECUDA, "cuTensorMapEncodeTiled failed (%d) for E tile %dx%d of %dx%d",
 				(int) r, g.TW, g.TH, g.SE, g.ny + 1);
+	return 0;
+}
+
+/* The six segment arrays of a species (one allocation, `astride` doubles apart) as a 2D tensor:
+ * dim 0 = slot, dim 1 = array; a box is one batch of 32 slots of the first `rows` arrays */
+static int
+make_segment_map(CUtensorMap *map, double *base, size_t nslot, size_t astride, int rows)
+{
+	static encode_fn encode = NULL;
+	if(!encode)
+	{
+		void *fn = NULL;
+		cudaDriverEntryPointQueryResult qres;
+		CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+		if(!fn || qres != cudaDriverEntryPointSuccess)
+			return fail(CPIC_B200_ECUDA, "cuTensorMapEncodeTiled is not available in this driver");
+		encode = (encode_fn) fn;
+	}
+	cuuint64_t dims[2] = { (cuuint64_t) nslot, 6 };
+	cuuint64_t strides[1] = { (cuuint64_t) astride * sizeof(double) };
+	cuuint32_t box[2] = { 32, (cuuint32_t) rows };
+	cuuint32_t estr[2] = { 1, 1 };
+	CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, dims, strides, box, estr,
+			CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+			CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	if(r != CUDA_SUCCESS)
+		return fail(CPIC_B200_ECUDA, "cuTensorMapEncodeTiled failed (%d) for the segments (%zu slots, stride %zu)", (int) r, nslot, astride);
 	return 0;
 }
 
@@ -464,8 +492,9 @@ alloc_species(sim_t_ *s, int is, int cap)
 		int ocs = (((int) ceil(cap * frac) + 31) / 32) * 32;
 		if(ocs < 32) ocs = 32;
 		const int occ = ((ocs / 4 + 31) / 32) * 32;
-		if((double) s->nb * cap >= 4294967296.0 || (double) s->nob * (4.0 * ocs + 4.0 * occ) >= 4294967296.0)
-			return fail(CPIC_B200_EINVAL, "species %d needs more than 2^32 particle slots on one GPU; lower capacity_factor / outbox_fraction or use more ranks", is);
+		/* slot numbers are 32-bit, and signed where they are TMA coordinates */
+		if((double) s->nb * cap >= 2147483648.0 || (double) s->nob * (4.0 * ocs + 4.0 * occ) >= 4294967296.0)
+			return fail(CPIC_B200_EINVAL, "species %d needs more than 2^31 particle slots on one GPU; lower capacity_factor / outbox_fraction or use more ranks", is);
 	}
 	int rc = alloc_species_storage(s, is, cap);
 	if(rc) free_species(h);      /* never leave a half-built species behind */
@@ -495,6 +524,12 @@ alloc_species_storage(sim_t_ *s, int is, int cap)
 	h.d.count = (int *) (b + 6 * arr);
 	h.d.cap = cap;
 	h.d.astride = (unsigned) (arr / sizeof(double));
+	if(!SEG_AOSOA)
+	{
+		int rc = make_segment_map(&h.segmap[0], h.d.x, nslot, arr / sizeof(double), 5);
+		if(!rc) rc = make_segment_map(&h.segmap[1], h.d.x, nslot, arr / sizeof(double), 6);
+		if(rc) return rc;
+	}
 
 	/* outbox regions: four sides of ocs slots, four corners of occ, stored code-major */
 	double frac = s->p.outbox_fraction > 0 ? s->p.outbox_fraction : 0.3;
@@ -1421,7 +1456,7 @@ launch_gather_push(sim_t_ *s, int is, cudaStream_t stream)
 	/* a push reads the pending arrivals and fills the other outbox */
 	const int cur = MODE == 0 ? h.arr : h.arr ^ 1;
 	k_gather_push<MODE><<<ctas, 32 * g.WPC, smem, stream>>>(h.d, g, push_params(s, is),
-			s->mapEx, s->mapEy, s->nb, cur, s->errflag);
+			s->mapEx, s->mapEy, h.segmap[0], h.segmap[1], s->nb, cur, s->errflag);
 	if(MODE != 0) h.arr = cur;
 	return check_launch(s);
 }
