@@ -545,20 +545,25 @@ def e2e_c_abi(env, sim, res, e_steps):
     import numpy as np
     L = sim.L
     params, nspecies, n_rank, n_total = res["params"], res["nspecies"], res["n_rank"], res["n_total"]
-    nbytes = L.cpic_b200_image_bytes(sim.h)
+    from cpic_b200._lib import check
+    banded = env.world == 1
+    bands = 16
+    nbytes = L.cpic_b200_banded_image_bytes(sim.h, bands) if banded else L.cpic_b200_image_bytes(sim.h)
+    assert nbytes > 0, L.cpic_b200_last_error()
     host = L.cpic_b200_host_alloc(nbytes)
     assert host, "pinned allocation failed"
     fields = {k: np.empty(sim.field_shape(k)) for k in ("rho", "phi", "Ex", "Ey")}
     fbytes = sum(a.nbytes for a in fields.values())
-    from cpic_b200._lib import check
-    check(L.cpic_b200_image_download(sim.h, host, nbytes))
-    pipelined = env.world == 1
+    if banded:
+        check(L.cpic_b200_banded_image_download(sim.h, host, nbytes, bands))
+    else:
+        check(L.cpic_b200_image_download(sim.h, host, nbytes))
     env.barrier()
     t0 = time.perf_counter()
     for _ in range(e_steps):
-        if pipelined:
-            # upload, step and download species by species on three streams (PCIe in both directions at once)
-            check(L.cpic_b200_step_host(sim.h, host, nbytes))
+        if banded:
+            # the image in bands of block rows: upload, push and download of the bands overlap (PCIe both ways at once)
+            check(L.cpic_b200_step_host_banded(sim.h, host, nbytes))
         else:
             check(L.cpic_b200_image_upload(sim.h, host, nbytes))
             sim.step()
@@ -573,8 +578,8 @@ def e2e_c_abi(env, sim, res, e_steps):
     moved = n_rank * 48 + 8 * nspecies + 4 * nspecies * nb
     return {"value": n_total * e_steps / te, "unit": UNIT, "h2d_bytes_per_step": int(moved),
             "d2h_bytes_per_step": int(moved + fbytes), "steps": e_steps, "ms_per_step": te / e_steps * 1e3,
-            "path": ("C ABI (cpic_b200_step_host: upload, sim_step and download of the image species by species on three "
-                     "streams; cpic_b200_get_field x 4)" if pipelined else
+            "path": (f"C ABI (cpic_b200_step_host_banded: the image in {bands} bands of block rows per species, each uploaded, "
+                     "pushed and downloaded as soon as its neighbours allow, on three streams; cpic_b200_get_field x 4)" if banded else
                      "C ABI (cpic_b200_image_upload, cpic_b200_step, cpic_b200_image_download, cpic_b200_get_field x 4)"),
             "note": "the whole particle state (x,y,ux,uy,uz,id of every particle) is uploaded from pinned host memory "
                     "before and downloaded after every sim_step, plus the four grids: host-owned particle lists, the "

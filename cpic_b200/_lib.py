@@ -91,6 +91,9 @@ EXPORTS = {
     "cpic_b200_image_download": (_i, [_vp, _vp, _i64]),
     "cpic_b200_image_upload": (_i, [_vp, _vp, _i64]),
     "cpic_b200_step_host": (_i, [_vp, _vp, _i64]),
+    "cpic_b200_banded_image_bytes": (_i64, [_vp, _i]),
+    "cpic_b200_banded_image_download": (_i, [_vp, _vp, _i64, _i]),
+    "cpic_b200_step_host_banded": (_i, [_vp, _vp, _i64]),
     "cpic_b200_host_alloc": (_vp, [C.c_size_t]),
     "cpic_b200_host_free": (None, [_vp]),
     "cpic_b200_conf_load": (_i, [C.c_char_p, _pp]),

@@ -535,7 +535,7 @@ __global__ void __launch_bounds__(32 * MAX_WPC, PUSH_MIN_CTAS)
 k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 		const __grid_constant__ CUtensorMap mapEx, const __grid_constant__ CUtensorMap mapEy,
 		const __grid_constant__ CUtensorMap mapS5, const __grid_constant__ CUtensorMap mapS6,
-		int nb, int cur, int *__restrict__ errflag)
+		int nb, int cur, int cta0, int *__restrict__ errflag)
 {
 	constexpr int NARR = PipeArrays<MODE>::N;
 	extern __shared__ __align__(128) unsigned char smem[];
@@ -550,7 +550,9 @@ k_gather_push(SpeciesDev sp, Geom g, PushParams pp,
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const unsigned lt = (1u << lane) - 1;
 	const int ncx = g.nbx / g.WPC;
-	const int by = blockIdx.x / ncx, cx = blockIdx.x % ncx;
+	/* cta0: a launch can take a band of block rows (cpic_b200_step_host_banded) */
+	const int cta = (int) blockIdx.x + cta0;
+	const int by = cta / ncx, cx = cta % ncx;
 	const int bx = cx * g.WPC + warp;
 	const int b = by * g.nbx + bx;
 	int *ocnt = wscratch + 18;       /* leavers per destination code so far */
@@ -1076,11 +1078,11 @@ k_regrow(SpeciesDev sp, SpeciesDev dst, Geom g, int nb, int arr)
  * clears the runs it consumed. Not on the per-step path: used before particles are
  * handed to the host (downloads, diagnostics). One warp per block. */
 static __global__ void __launch_bounds__(256)
-k_absorb(SpeciesDev sp, Geom g, int nb, int arr, int *__restrict__ errflag)
+k_absorb(SpeciesDev sp, Geom g, int nb, int arr, int *__restrict__ errflag, int b0, int b1)
 {
 	const int lane = threadIdx.x & 31;
-	const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-	if(b >= nb) return;
+	const int b = b0 + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);     /* blocks [b0, b1) */
+	if(b >= b1) return;
 	__shared__ int scratch[8][18];
 	const Outbox &in = sp.ob[arr];
 	const Arrivals A = find_arrivals(in, sp.nob, g, nb, b, lane, scratch[threadIdx.x >> 5]);
@@ -1365,6 +1367,31 @@ k_image_copy(SpeciesDev sp, int nb, const int *__restrict__ cnt, const long long
 		}
 	__syncwarp();                /* every lane has read the old count */
 	if(pack <= 0 && lane == 0) sp.count[b] = at + c;
+}
+
+/* k_image_copy for a band of blocks [b0, b0 + nblk): `cnt` and `off` are band-local (entry 0 = block b0),
+ * the band's image holds `stride` slots per array. pack 1: segments -> image (cnt = the device counts of
+ * the band); 0: image -> segments, replacing their content. */
+static __global__ void __launch_bounds__(256)
+k_band_copy(SpeciesDev sp, int b0, int nblk, const int *__restrict__ cnt, const long long *__restrict__ off,
+		double *__restrict__ img, long long stride, int pack, int *__restrict__ errflag)
+{
+	const int lane = threadIdx.x & 31;
+	const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	if(k >= nblk) return;
+	const int b = b0 + k;
+	const int c = cnt[k];
+	const long long o = off[k];
+	if(o + c > stride) { if(lane == 0) atomicOr(errflag, 1); return; }      /* the band outgrew its image */
+	double *arr[6] = { sp.x, sp.y, sp.ux, sp.uy, sp.uz, (double *) sp.id };
+#pragma unroll
+	for(int a = 0; a < 6; a++)
+		for(int i = lane; i < c; i += 32)
+		{
+			if(pack) img[(size_t) a * stride + o + i] = arr[a][seg_slot(sp.cap, b, i)];
+			else arr[a][seg_slot(sp.cap, b, i)] = img[(size_t) a * stride + o + i];
+		}
+	if(!pack && lane == 0) sp.count[b] = c;
 }
 
 /* Exclusive prefix of the block counts (the offsets of the compact image), by one CTA: every thread

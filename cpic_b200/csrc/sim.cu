@@ -96,6 +96,8 @@ struct cpic_b200_sim {
 	size_t hstage_cap[2][CPIC_B200_MAX_SPECIES];
 	long long *hoff[2][CPIC_B200_MAX_SPECIES];       /* block offsets of those images (nb + 1) */
 	int *hcnt[CPIC_B200_MAX_SPECIES];                /* uploaded block counts */
+	long long *h_band;                               /* pinned: new totals of the bands, far-mover counts */
+	cudaEvent_t ev_band[CPIC_B200_MAX_SPECIES][2 * 64];      /* banded step: [species][uploaded j | packed 64 + j] */
 	cudaEvent_t ev_fork, ev_join;
 	bool overlap_species;
 	int device;
@@ -446,7 +448,9 @@ cpic_b200_destroy(cpic_b200_sim_t *s)
 		if(s->ev_packed[i]) cudaEventDestroy(s->ev_packed[i]);
 		for(int k = 0; k < 2; k++) { cudaFree(s->hstage[k][i]); cudaFree(s->hoff[k][i]); }
 		cudaFree(s->hcnt[i]);
+		for(int k = 0; k < 128; k++) if(s->ev_band[i][k]) cudaEventDestroy(s->ev_band[i][k]);
 	}
+	if(s->h_band) cudaFreeHost(s->h_band);
 	if(s->ev_fork) cudaEventDestroy(s->ev_fork);
 	if(s->ev_join) cudaEventDestroy(s->ev_join);
 	delete s;
@@ -1166,7 +1170,7 @@ absorb(sim_t_ *s, int is)
 	 * ranks the capacity is a collective decision, so it is an error here. */
 	int *flag = s->errflag + 15;
 	CK(cudaMemsetAsync(flag, 0, sizeof(int), s->stream));
-	k_absorb<<<(s->nb + 7) / 8, 256, 0, s->stream>>>(h.d, s->g, s->nb, h.arr, flag);
+	k_absorb<<<(s->nb + 7) / 8, 256, 0, s->stream>>>(h.d, s->g, s->nb, h.arr, flag, 0, s->nb);
 	{
 		cudaError_t e = cudaGetLastError();
 		if(e != cudaSuccess) return fail(CPIC_B200_ECUDA, "kernel launch failed: %s", cudaGetErrorString(e));
@@ -1444,20 +1448,23 @@ push_params(const sim_t_ *s, int is)
 	return pp;
 }
 
+/* row0, rows >= 0: only the block rows [row0, row0 + rows) (a band); the caller flips h.arr once all
+ * bands of the step are out */
 template <int MODE>
 static int
-launch_gather_push(sim_t_ *s, int is, cudaStream_t stream)
+launch_gather_push(sim_t_ *s, int is, cudaStream_t stream, int row0 = -1, int rows = 0)
 {
 	SpeciesHost &h = s->sp[is];
 	if(!h.block) return 0;
 	const Geom &g = s->g;
 	const size_t smem = push_smem_bytes<MODE>(s);
-	const int ctas = s->nb / g.WPC;
+	const int ncx = g.nbx / g.WPC;
+	const int ctas = row0 < 0 ? s->nb / g.WPC : rows * ncx;
 	/* a push reads the pending arrivals and fills the other outbox */
 	const int cur = MODE == 0 ? h.arr : h.arr ^ 1;
 	k_gather_push<MODE><<<ctas, 32 * g.WPC, smem, stream>>>(h.d, g, push_params(s, is),
-			s->mapEx, s->mapEy, h.segmap[0], h.segmap[1], s->nb, cur, s->errflag);
-	if(MODE != 0) h.arr = cur;
+			s->mapEx, s->mapEy, h.segmap[0], h.segmap[1], s->nb, cur, row0 < 0 ? 0 : row0 * ncx, s->errflag);
+	if(MODE != 0 && row0 < 0) h.arr = cur;
 	return check_launch(s);
 }
 
@@ -2047,7 +2054,7 @@ cpic_b200_step_host(cpic_b200_sim_t *s, void *host, int64_t bytes)
 				CK(cudaMalloc(&s->hstage[k][is], (size_t) 6 * (size_t) u.n * sizeof(double)));
 				s->hstage_cap[k][is] = (size_t) 6 * (size_t) u.n;
 			}
-			if(!s->hoff[k][is]) CK(cudaMalloc(&s->hoff[k][is], ((size_t) s->nb + 1) * sizeof(long long)));
+			if(!s->hoff[k][is]) CK(cudaMalloc(&s->hoff[k][is], ((size_t) s->nb + 64 + 1) * sizeof(long long)));
 		}
 		if(!s->hcnt[is]) CK(cudaMalloc(&s->hcnt[is], (size_t) s->nb * sizeof(int)));
 		/* upload: counts, offsets, the six arrays */
@@ -2075,7 +2082,7 @@ cpic_b200_step_host(cpic_b200_sim_t *s, void *host, int64_t bytes)
 		SpeciesSet set;
 		set.sp[0] = h.d; set.arr[0] = h.arr; set.n = 1;
 		k_far_insert<<<1, 1024, 0, s->stream>>>(set, s->g, s->errflag);
-		k_absorb<<<(s->nb + 7) / 8, 256, 0, s->stream>>>(h.d, s->g, s->nb, h.arr, flag);
+		k_absorb<<<(s->nb + 7) / 8, 256, 0, s->stream>>>(h.d, s->g, s->nb, h.arr, flag, 0, s->nb);
 		k_count_offsets<<<1, 1024, 0, s->stream>>>(h.d.count, s->nb, s->hoff[1][is]);
 		k_image_copy<<<(s->nb + 7) / 8, 256, 0, s->stream>>>(h.d, s->nb, h.d.count, s->hoff[1][is], s->hstage[1][is], u.n, 1);
 		if((rc = check_launch(s, 4))) return rc;
@@ -2094,6 +2101,343 @@ cpic_b200_step_host(cpic_b200_sim_t *s, void *host, int64_t bytes)
 	if(s->h_err[15])
 		return fail(CPIC_B200_ECAPACITY, "a particle block could not take its arrivals during cpic_b200_step_host: "
 				"raise capacity_factor (now %g)", s->p.capacity_factor);
+	return cpic_b200_sync(s);
+}
+
+/* ---- the host image in bands of block rows (cpic_b200_step_host_banded) ----
+ * Layout: int64 magic, bands, species, blocks; then per species that holds particles, per band j:
+ * int64 n, int64 cap, int32 counts[blocks of the band] (padded to 8 bytes), double arrays[6][cap]
+ * (x y ux uy uz id; `cap` >= n leaves room for the band's population to change). */
+#define BAND_MAGIC 0x31444e4243495043LL      /* "CPICBND1" */
+#define BAND_MAX 64
+
+struct BandView {
+	int64_t *n, *cap;
+	int *cnt;
+	double *data;
+	int b0, nblk;
+	size_t stage;            /* first double of the band in the species' device staging */
+};
+
+static void
+band_rows(const sim_t_ *s, int bands, int j, int *b0, int *nblk)
+{
+	const int r0 = (int) ((long long) s->g.nby * j / bands), r1 = (int) ((long long) s->g.nby * (j + 1) / bands);
+	*b0 = r0 * s->g.nbx;
+	*nblk = (r1 - r0) * s->g.nbx;
+}
+
+/* Walks the image: fills view[species][band]; with `caps` (from cpic_b200_banded_image_bytes) lays it out */
+static int
+band_views(sim_t_ *s, char *host, int64_t bytes, int bands, BandView view[][BAND_MAX], size_t stage_total[], bool create,
+		const std::vector<std::vector<int64_t>> *caps)
+{
+	char *p = host, *end = host + bytes;
+	if(p + 32 > end) return fail(CPIC_B200_EINVAL, "truncated banded image");
+	int64_t *hdr = (int64_t *) p;
+	if(create) { hdr[0] = BAND_MAGIC; hdr[1] = bands; hdr[2] = s->p.nspecies; hdr[3] = s->nb; }
+	else if(hdr[0] != BAND_MAGIC || hdr[1] != bands || hdr[2] != s->p.nspecies || hdr[3] != s->nb)
+		return fail(CPIC_B200_EINVAL, "not a banded image of this simulation");
+	p += 32;
+	for(int is = 0; is < s->p.nspecies; is++)
+	{
+		stage_total[is] = 0;
+		if(!s->sp[is].block) continue;
+		for(int j = 0; j < bands; j++)
+		{
+			BandView &v = view[is][j];
+			band_rows(s, bands, j, &v.b0, &v.nblk);
+			if(p + 16 > end) return fail(CPIC_B200_EINVAL, "truncated banded image");
+			v.n = (int64_t *) p; v.cap = v.n + 1; p += 16;
+			if(create) { *v.cap = (*caps)[(size_t) is][(size_t) j]; *v.n = 0; }
+			v.cnt = (int *) p; p += ((size_t) v.nblk * 4 + 7) & ~(size_t) 7;
+			v.data = (double *) p;
+			if(*v.cap < 0 || *v.n < 0 || *v.n > *v.cap || p + 6 * 8 * *v.cap > end) return fail(CPIC_B200_EINVAL, "truncated banded image");
+			p += 6 * 8 * *v.cap;
+			v.stage = stage_total[is];
+			stage_total[is] += (size_t) 6 * (size_t) *v.cap;
+		}
+	}
+	return 0;
+}
+
+static int
+band_choose(const sim_t_ *s, int bands)
+{
+	if(bands < 1) bands = 8;
+	if(bands > BAND_MAX) bands = BAND_MAX;
+	if(bands > s->g.nby) bands = s->g.nby;
+	return bands;
+}
+
+/* per-band capacities from the present block counts: a quarter of slack */
+static int
+band_caps(sim_t_ *s, int bands, std::vector<std::vector<int64_t>> &caps)
+{
+	caps.assign((size_t) s->p.nspecies, std::vector<int64_t>());
+	std::vector<int> cnt((size_t) s->nb);
+	for(int is = 0; is < s->p.nspecies; is++)
+	{
+		SpeciesHost &h = s->sp[is];
+		if(!h.block) continue;
+		int rc = absorb(s, is);
+		if(rc) return rc;
+		CK(cudaMemcpyAsync(cnt.data(), h.d.count, cnt.size() * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+		CK(cudaStreamSynchronize(s->stream));
+		for(int j = 0; j < bands; j++)
+		{
+			int b0, nblk;
+			band_rows(s, bands, j, &b0, &nblk);
+			int64_t n = 0;
+			for(int b = b0; b < b0 + nblk; b++) n += cnt[(size_t) b];
+			caps[(size_t) is].push_back((n + n / 4 + 4096 + 31) / 32 * 32);
+		}
+	}
+	return 0;
+}
+
+extern "C" int64_t
+cpic_b200_banded_image_bytes(cpic_b200_sim_t *s, int bands)
+{
+	if(!s) return -1;
+	cudaSetDevice(s->device);
+	bands = band_choose(s, bands);
+	std::vector<std::vector<int64_t>> caps;
+	if(band_caps(s, bands, caps)) return -1;
+	int64_t bytes = 32;
+	for(int is = 0; is < s->p.nspecies; is++)
+		for(size_t j = 0; j < caps[(size_t) is].size(); j++)
+		{
+			int b0, nblk;
+			band_rows(s, bands, (int) j, &b0, &nblk);
+			bytes += 16 + (((int64_t) nblk * 4 + 7) & ~7LL) + 6 * 8 * caps[(size_t) is][j];
+		}
+	return bytes;
+}
+
+static int
+band_staging(sim_t_ *s, const size_t stage_total[])
+{
+	for(int is = 0; is < s->p.nspecies; is++)
+	{
+		if(!s->sp[is].block) continue;
+		for(int k = 0; k < 2; k++)
+		{
+			if(s->hstage_cap[k][is] < stage_total[is])
+			{
+				cudaFree(s->hstage[k][is]);
+				s->hstage[k][is] = NULL; s->hstage_cap[k][is] = 0;
+				CK(cudaMalloc(&s->hstage[k][is], stage_total[is] * sizeof(double)));
+				s->hstage_cap[k][is] = stage_total[is];
+			}
+			/* band-local offsets: nblk + 1 entries per band */
+			if(!s->hoff[k][is]) CK(cudaMalloc(&s->hoff[k][is], ((size_t) s->nb + BAND_MAX + 1) * sizeof(long long)));
+		}
+		if(!s->hcnt[is]) CK(cudaMalloc(&s->hcnt[is], (size_t) s->nb * sizeof(int)));
+	}
+	if(!s->h_band) CK(cudaMallocHost(&s->h_band, (size_t) CPIC_B200_MAX_SPECIES * (BAND_MAX + 1) * sizeof(long long)));
+	if(!s->stream_in)
+	{
+		CK(cudaStreamCreateWithFlags(&s->stream_in, cudaStreamNonBlocking));
+		CK(cudaStreamCreateWithFlags(&s->stream_out, cudaStreamNonBlocking));
+		for(int i = 0; i < CPIC_B200_MAX_SPECIES; i++)
+		{
+			CK(cudaEventCreateWithFlags(&s->ev_up[i], cudaEventDisableTiming));
+			CK(cudaEventCreateWithFlags(&s->ev_packed[i], cudaEventDisableTiming));
+		}
+	}
+	for(int i = 0; i < CPIC_B200_MAX_SPECIES; i++)
+		for(int k = 0; k < 2 * BAND_MAX; k++)
+			if(!s->ev_band[i][k]) CK(cudaEventCreateWithFlags(&s->ev_band[i][k], cudaEventDisableTiming));
+	return 0;
+}
+
+/* absorb + offsets + pack of band j of one species on the compute stream; the band's new total lands in
+ * the pinned word `total`; records ev_band[is][64 + j] */
+static int
+band_pack(sim_t_ *s, int is, int j, const BandView &v, int *flag)
+{
+	SpeciesHost &h = s->sp[is];
+	long long *off = s->hoff[1][is] + v.b0 + j;
+	k_absorb<<<(v.nblk + 7) / 8, 256, 0, s->stream>>>(h.d, s->g, s->nb, h.arr, flag, v.b0, v.b0 + v.nblk);
+	k_count_offsets<<<1, 1024, 0, s->stream>>>(h.d.count + v.b0, v.nblk, off);
+	k_band_copy<<<(v.nblk + 7) / 8, 256, 0, s->stream>>>(h.d, v.b0, v.nblk, h.d.count + v.b0, off,
+			s->hstage[1][is] + v.stage, *v.cap, 1, flag);
+	int rc = check_launch(s, 3);
+	if(rc) return rc;
+	CK(cudaMemcpyAsync(s->h_band + (size_t) is * (BAND_MAX + 1) + j, off + v.nblk, sizeof(long long), cudaMemcpyDeviceToHost, s->stream));
+	CK(cudaEventRecord(s->ev_band[is][BAND_MAX + j], s->stream));
+	return 0;
+}
+
+/* the packed band goes to the host image (after its event): counts and the six arrays */
+static int
+band_download(sim_t_ *s, int is, int j, const BandView &v)
+{
+	SpeciesHost &h = s->sp[is];
+	CK(cudaEventSynchronize(s->ev_band[is][BAND_MAX + j]));
+	const long long n = s->h_band[(size_t) is * (BAND_MAX + 1) + j];
+	if(n < 0 || n > *v.cap)
+		return fail(CPIC_B200_ECAPACITY, "species %d: band %d holds %lld particles, its image %lld: make a new image", is, j, n, (long long) *v.cap);
+	*v.n = n;
+	CK(cudaStreamWaitEvent(s->stream_out, s->ev_band[is][BAND_MAX + j], 0));
+	CK(cudaMemcpyAsync(v.cnt, h.d.count + v.b0, (size_t) v.nblk * sizeof(int), cudaMemcpyDeviceToHost, s->stream_out));
+	for(int a = 0; a < 6; a++)
+		CK(cudaMemcpyAsync(v.data + (size_t) a * *v.cap, s->hstage[1][is] + v.stage + (size_t) a * *v.cap, (size_t) n * sizeof(double),
+					cudaMemcpyDeviceToHost, s->stream_out));
+	return 0;
+}
+
+/* The present state as a banded image (bands <= 0: 8) */
+extern "C" int
+cpic_b200_banded_image_download(cpic_b200_sim_t *s, void *host, int64_t bytes, int bands)
+{
+	if(!s || !host) return fail(CPIC_B200_EINVAL, "null argument");
+	CK(cudaSetDevice(s->device));
+	bands = band_choose(s, bands);
+	std::vector<std::vector<int64_t>> caps;
+	int rc = band_caps(s, bands, caps);
+	if(rc) return rc;
+	static BandView view[CPIC_B200_MAX_SPECIES][BAND_MAX];
+	size_t stage_total[CPIC_B200_MAX_SPECIES];
+	if((rc = band_views(s, (char *) host, bytes, bands, view, stage_total, true, &caps))) return rc;
+	if((rc = band_staging(s, stage_total))) return rc;
+	int *flag = s->errflag + 15;
+	CK(cudaMemsetAsync(flag, 0, sizeof(int), s->stream));
+	for(int is = 0; is < s->p.nspecies; is++)
+	{
+		if(!s->sp[is].block) continue;
+		for(int j = 0; j < bands; j++)
+		{
+			if((rc = band_pack(s, is, j, view[is][j], flag))) return rc;
+			if((rc = band_download(s, is, j, view[is][j]))) return rc;
+		}
+	}
+	CK(cudaMemcpyAsync(s->h_err + 15, flag, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+	CK(cudaStreamSynchronize(s->stream_out));
+	CK(cudaStreamSynchronize(s->stream));
+	if(s->h_err[15]) return fail(CPIC_B200_ECAPACITY, "a band outgrew its image");
+	return 0;
+}
+
+/* One sim_step with the particle state in pinned host memory, in bands of block rows: a band is
+ * uploaded, unpacked and pushed while the next ones are still on their way, and as soon as its
+ * neighbour bands are pushed too its arrivals are absorbed and it is packed and downloaded -- uploads
+ * and downloads overlap all along (cpic_b200_step_host overlaps species only). Band 0 closes the ring
+ * with the last band and goes last. Far movers (rare) are placed when every band is pushed: if there
+ * were any, the species is packed and downloaded again. One rank. */
+extern "C" int
+cpic_b200_step_host_banded(cpic_b200_sim_t *s, void *host, int64_t bytes)
+{
+	if(!s || !host) return fail(CPIC_B200_EINVAL, "null argument");
+	if(s->iter < 0) return fail(CPIC_B200_EINVAL, "call cpic_b200_pre_step first");
+	if(s->comm) return fail(CPIC_B200_EINVAL, "cpic_b200_step_host_banded runs on one rank");
+	CK(cudaSetDevice(s->device));
+	if(bytes < 32 || ((int64_t *) host)[0] != BAND_MAGIC) return fail(CPIC_B200_EINVAL, "not a banded image");
+	const int bands = (int) ((int64_t *) host)[1];
+	if(bands < 1 || bands > BAND_MAX || bands > s->g.nby) return fail(CPIC_B200_EINVAL, "bad number of bands");
+	static BandView view[CPIC_B200_MAX_SPECIES][BAND_MAX];
+	size_t stage_total[CPIC_B200_MAX_SPECIES];
+	int rc = band_views(s, (char *) host, bytes, bands, view, stage_total, false, NULL);
+	if(rc) return rc;
+	if((rc = band_staging(s, stage_total))) return rc;
+	CK(cudaStreamSynchronize(s->stream));
+	const Geom &g = s->g;
+	std::vector<std::vector<long long>> off((size_t) s->p.nspecies * bands);
+
+	/* uploads: every band of every species, in the order they are used */
+	for(int is = 0; is < s->p.nspecies; is++)
+	{
+		SpeciesHost &h = s->sp[is];
+		if(!h.block) continue;
+		for(int j = 0; j < bands; j++)
+		{
+			const BandView &v = view[is][j];
+			std::vector<long long> &o = off[(size_t) is * bands + j];
+			o.resize((size_t) v.nblk + 1);
+			long long m = 0;
+			for(int k = 0; k < v.nblk; k++)
+			{
+				if(v.cnt[k] < 0 || v.cnt[k] > h.d.cap) return fail(CPIC_B200_ECAPACITY, "image block %d holds %d particles, capacity %d", v.b0 + k, v.cnt[k], h.d.cap);
+				o[(size_t) k] = m; m += v.cnt[k];
+			}
+			o[(size_t) v.nblk] = m;
+			if(m != *v.n) return fail(CPIC_B200_EINVAL, "image counts of band %d do not add up", j);
+			CK(cudaMemcpyAsync(s->hcnt[is] + v.b0, v.cnt, (size_t) v.nblk * sizeof(int), cudaMemcpyHostToDevice, s->stream_in));
+			CK(cudaMemcpyAsync(s->hoff[0][is] + v.b0 + j, o.data(), o.size() * sizeof(long long), cudaMemcpyHostToDevice, s->stream_in));
+			for(int a = 0; a < 6; a++)
+				CK(cudaMemcpyAsync(s->hstage[0][is] + v.stage + (size_t) a * *v.cap, v.data + (size_t) a * *v.cap, (size_t) *v.n * sizeof(double),
+							cudaMemcpyHostToDevice, s->stream_in));
+			CK(cudaEventRecord(s->ev_band[is][j], s->stream_in));
+		}
+	}
+	/* the fields of this step do not depend on the upload */
+	if((rc = cpic_b200_stage_field_E(s))) return rc;
+	int *flag = s->errflag + 15;
+	CK(cudaMemsetAsync(flag, 0, sizeof(int), s->stream));
+	for(int is = 0; is < s->p.nspecies; is++)
+	{
+		SpeciesHost &h = s->sp[is];
+		if(!h.block) continue;
+		/* the image holds every particle: no arrivals are pending */
+		for(int k = 0; k < 2; k++) CK(cudaMemsetAsync(h.d.ob[k].count, 0, (size_t) s->nob * 9 * sizeof(int), s->stream));
+		const int cur = h.arr ^ 1;
+		for(int j = 0; j < bands; j++)
+		{
+			const BandView &v = view[is][j];
+			CK(cudaStreamWaitEvent(s->stream, s->ev_band[is][j], 0));
+			k_band_copy<<<(v.nblk + 7) / 8, 256, 0, s->stream>>>(h.d, v.b0, v.nblk, s->hcnt[is] + v.b0, s->hoff[0][is] + v.b0 + j,
+					s->hstage[0][is] + v.stage, *v.cap, 0, flag);
+			if((rc = check_launch(s))) return rc;
+			if((rc = launch_gather_push<2>(s, is, s->stream, v.b0 / g.nbx, v.nblk / g.nbx))) return rc;
+			/* band j-1 has all its neighbours pushed now (band 0 waits for the last one) */
+			if(j >= 2)
+			{
+				h.arr = cur;         /* k_absorb reads the outbox this push fills */
+				if((rc = band_pack(s, is, j - 1, view[is][j - 1], flag))) return rc;
+				h.arr = cur ^ 1;
+			}
+		}
+		h.arr = cur;
+		/* far movers of the whole species: their number first (pinned), then their placement */
+		CK(cudaMemcpyAsync(s->h_band + (size_t) is * (BAND_MAX + 1) + BAND_MAX, h.d.fcount, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+		SpeciesSet set;
+		set.sp[0] = h.d; set.arr[0] = h.arr; set.n = 1;
+		k_far_insert<<<1, 1024, 0, s->stream>>>(set, g, s->errflag);
+		if((rc = check_launch(s))) return rc;
+		if(bands >= 2) { if((rc = band_pack(s, is, bands - 1, view[is][bands - 1], flag))) return rc; }
+		if((rc = band_pack(s, is, 0, view[is][0], flag))) return rc;
+	}
+	if((rc = cpic_b200_stage_field_rho(s))) return rc;
+	s->iter++;
+	CK(cudaMemcpyAsync(s->h_err + 15, flag, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+
+	/* downloads, band by band as they are packed: 1 .. bands-1, then 0 */
+	for(int is = 0; is < s->p.nspecies; is++)
+	{
+		SpeciesHost &h = s->sp[is];
+		if(!h.block) continue;
+		for(int k = 1; k <= bands; k++)
+			if((rc = band_download(s, is, k % bands, view[is][k % bands]))) return rc;
+		/* the far-mover count was copied before the last bands were packed */
+		const int nfar = *(const int *) (s->h_band + (size_t) is * (BAND_MAX + 1) + BAND_MAX);
+		if(nfar > 0)
+		{
+			/* k_far_insert appended particles to blocks that were packed before: once more, in order */
+			CK(cudaStreamSynchronize(s->stream_out));
+			for(int j = 0; j < bands; j++)
+			{
+				if((rc = band_pack(s, is, j, view[is][j], flag))) return rc;
+				if((rc = band_download(s, is, j, view[is][j]))) return rc;
+			}
+		}
+	}
+	CK(cudaStreamSynchronize(s->stream_in));
+	CK(cudaStreamSynchronize(s->stream_out));
+	CK(cudaStreamSynchronize(s->stream));
+	if(s->h_err[15])
+		return fail(CPIC_B200_ECAPACITY, "a particle block or a band of the image overflowed during cpic_b200_step_host_banded: "
+				"raise capacity_factor (now %g) or make a new image", s->p.capacity_factor);
 	return cpic_b200_sync(s);
 }
 

@@ -212,6 +212,14 @@ int cpic_b200_image_upload(cpic_b200_sim_t *sim, const void *host, int64_t bytes
  * (the upload of one species overlaps the push and the download of the previous one: PCIe runs in both
  * directions at once); the image comes back with the new block counts and particles. One rank. */
 int cpic_b200_step_host(cpic_b200_sim_t *sim, void *host, int64_t bytes);
+/* The same in bands of block rows: the image is laid out band by band (cpic_b200_banded_image_download;
+ * bands <= 0: 8), every band is uploaded, unpacked and pushed while the next ones are on their way, and
+ * absorbed, packed and downloaded as soon as its neighbour bands are pushed: uploads and downloads overlap
+ * all along. A band's image has a quarter of slack for its population to change; a band that outgrows it
+ * fails with CPIC_B200_ECAPACITY (make a new image). One rank. */
+int64_t cpic_b200_banded_image_bytes(cpic_b200_sim_t *sim, int bands);
+int cpic_b200_banded_image_download(cpic_b200_sim_t *sim, void *host, int64_t bytes, int bands);
+int cpic_b200_step_host_banded(cpic_b200_sim_t *sim, void *host, int64_t bytes);
 void *cpic_b200_host_alloc(size_t bytes);   /* pinned */
 void cpic_b200_host_free(void *p);
 

@@ -291,3 +291,75 @@ def test_step_with_the_state_in_host_memory():
         L.cpic_b200_host_free(host)
         a.close()
         b.close()
+
+
+@pytest.mark.parametrize("conf,bands", [("2d-2species-small.conf", 4), ("far-beam.conf", 3), ("uniform-small.conf", 8), ("two-streams.conf", 1)])
+def test_banded_step_with_the_state_in_host_memory(conf, bands):
+    """cpic_b200_step_host_banded: the image in bands of block rows, every band uploaded, pushed, absorbed,
+    packed and downloaded as soon as its neighbours allow (far movers: the species is packed again) -- the
+    state of a resident cpic_b200_step to 1e-12, and the image holds exactly the device's particles."""
+    import ctypes as C
+    path = conf_path(conf)
+    a = Sim.from_conf(path)
+    b = Sim.from_conf(path)
+    L = b.L
+    nbytes = L.cpic_b200_banded_image_bytes(b.h, bands)
+    assert nbytes > 0
+    host = L.cpic_b200_host_alloc(nbytes)
+    assert host
+    try:
+        assert L.cpic_b200_banded_image_download(b.h, host, nbytes, bands) == 0, L.cpic_b200_last_error()
+        for it in range(8):
+            a.step()
+            rc = L.cpic_b200_step_host_banded(b.h, host, nbytes)
+            assert rc == 0, L.cpic_b200_last_error()
+        a.sync()
+        assert b.iter == a.iter
+        for k in ("rho", "phi", "Ex", "Ey"):
+            assert relerr(b.raw_field(k)[:, :a.params.nx], a.raw_field(k)[:, :a.params.nx]) <= TOL, k
+        for i in range(a.nspecies):
+            pa, pb = a.particles(i), b.particles(i)
+            assert np.array_equal(pa["id"], pb["id"])
+            for k, scale in (("x", a.params.Lx), ("y", a.params.Ly), ("ux", np.abs(pa["ux"]).max()), ("uy", np.abs(pa["uy"]).max())):
+                assert np.abs(pa[k] - pb[k]).max() / max(scale, 1e-300) <= TOL, (i, k)
+        # the image: header, then per species and band n, cap, counts, six arrays of cap entries
+        raw = np.frombuffer((C.c_char * nbytes).from_address(host), np.uint8)
+        hdr = raw[:32].view(np.int64)
+        assert hdr[1] == min(bands, hdr[3]) or hdr[1] <= bands
+        off, nb_total = 32, int(hdr[3])
+        nbands = int(hdr[1])
+        for i in range(a.nspecies):
+            ids = []
+            for j in range(nbands):
+                n, cap = (int(v) for v in raw[off:off + 16].view(np.int64))
+                off += 16
+                r0, r1 = b_rows(a, nbands, j), b_rows(a, nbands, j + 1)
+                nblk = (r1 - r0) * nbx_of(a)
+                cnt = raw[off:off + 4 * nblk].view(np.int32)
+                assert cnt.sum() == n
+                off += (4 * nblk + 7) // 8 * 8
+                arr = raw[off:off + 48 * cap].view(np.float64).reshape(6, cap)
+                ids.append(arr[5, :n].view(np.int64).copy())
+                off += 48 * cap
+            ids = np.sort(np.concatenate(ids))
+            assert np.array_equal(ids, np.sort(b.particles(i)["id"]))
+    finally:
+        L.cpic_b200_host_free(host)
+        a.close()
+        b.close()
+
+
+def nbx_of(sim):
+    return sim.params.nx // 8 if sim.params.nx % 8 == 0 else sim.params.nx // _blk(sim.params.nx)
+
+
+def _blk(n):
+    d = 8
+    while d > 1 and n % d:
+        d >>= 1
+    return d
+
+
+def b_rows(sim, bands, j):
+    nby = sim.params.ny // _blk(sim.params.ny)
+    return nby * j // bands
