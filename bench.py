@@ -547,7 +547,7 @@ def e2e_c_abi(env, sim, res, e_steps):
     params, nspecies, n_rank, n_total = res["params"], res["nspecies"], res["n_rank"], res["n_total"]
     from cpic_b200._lib import check
     banded = env.world == 1
-    bands = 16
+    bands = int(min(16, max(4, n_rank * 48 // (256 << 20))))      # ~256 MB of particles per band
     nbytes = L.cpic_b200_banded_image_bytes(sim.h, bands) if banded else L.cpic_b200_image_bytes(sim.h)
     assert nbytes > 0, L.cpic_b200_last_error()
     host = L.cpic_b200_host_alloc(nbytes)
