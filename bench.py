@@ -698,9 +698,20 @@ def main():
         clk["window"] = "warm-up + timed region + repeats of the same steps of the main workload"
     roofline = res["roofline"]
     if world == 1 and args.workload in ("A", "D"):
-        roofline["traffic"] = ncu_traffic(path=os.path.join(ROOT, "profiles", f"r2_ncu_full_summary_{args.workload}.csv"))
+        csvp = os.path.join(ROOT, "profiles", f"r2_ncu_full_summary_{args.workload}.csv")
+        roofline["traffic"] = ncu_traffic(path=csvp)
         roofline["traffic_source"] = (f"profiles/r2_ncu_full_summary_{args.workload}.csv (ncu --set full of this workload, "
                                       "dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the species)")
+        if roofline["traffic"]:
+            # what the kernel really moves against the same peak (the algorithmic figure is `frac`)
+            roofline["traffic_over_algorithmic"] = roofline["traffic"] / (BYTES_GATHER_PUSH * res["nps"])
+            roofline["dram_frac"] = roofline["traffic"] / (roofline["avg_launch_ms"] * 1e-3) / 1e9 / roofline["peak"]
+        td = ncu_traffic(kernel="k_deposit", path=csvp)
+        for k, v in roofline["other_kernels"].items():
+            if k.startswith("k_deposit") and td:
+                v["traffic"] = td
+                v["traffic_over_algorithmic"] = td / (BYTES_DEPOSIT * res["n_rank"])
+                v["dram_frac"] = td / (v["avg_launch_ms"] * 1e-3) / 1e9 / roofline["peak"]
     else:
         roofline["traffic"] = None
 
