@@ -238,6 +238,105 @@ now(void)
 	return (double) t.tv_sec + 1e-9 * (double) t.tv_nsec;
 }
 
+static int
+env_int(const char *name, int fallback)
+{
+	const char *e = getenv(name);
+	return (e && *e) ? atoi(e) : fallback;
+}
+
+/* MPI_Bcast of the NCCL id without MPI: rank 0 writes it to a file (written under another name, then
+ * renamed: readers never see a partial file), the others wait for the file */
+static int
+share_id(int rank, unsigned char id[128])
+{
+	char path[4096], tmp[4200];
+	const char *e = getenv("CPIC_B200_ID_FILE");
+	if(e && *e) snprintf(path, sizeof(path), "%s", e);
+	else snprintf(path, sizeof(path), "/tmp/cpic_b200_id_%s_%ld", getenv("MASTER_PORT") ? getenv("MASTER_PORT") : "0", (long) getppid());
+	if(rank == 0)
+	{
+		if(cpic_b200_comm_id(id)) return -1;
+		snprintf(tmp, sizeof(tmp), "%s.tmp", path);
+		FILE *f = fopen(tmp, "wb");
+		if(!f || fwrite(id, 1, 128, f) != 128) { front_set_error("cannot write %s", tmp); if(f) fclose(f); return -1; }
+		fclose(f);
+		if(rename(tmp, path)) { front_set_error("cannot rename %s", tmp); return -1; }
+		return 0;
+	}
+	for(int tries = 0; tries < 6000; tries++)
+	{
+		FILE *f = fopen(path, "rb");
+		if(f)
+		{
+			const size_t n = fread(id, 1, 128, f);
+			fclose(f);
+			if(n == 128) return 0;
+		}
+		usleep(20000);
+	}
+	front_set_error("rank %d: no communicator id in %s after two minutes", rank, path);
+	return -1;
+}
+
+/* sim_init + sim_run of one rank among several (Y slabs, src/sim.c:116-130, 177-187): the reference's initial
+ * conditions drawn on the device for this rank's slab, the exchanges inside the library */
+static int
+run_ranks(const char *fn, int rank, int nranks, int device, double t0)
+{
+	cpic_b200_sim_t *sim = NULL;
+	cpic_b200_run_t run;
+	unsigned char id[128];
+	if(cpic_b200_sim_from_conf_device(fn, rank, nranks, device, 1, 1 << 22, &sim, &run))
+	{
+		fprintf(stderr, "sim_init failed\n%s\n", cpic_b200_last_error());
+		return 1;
+	}
+	if(share_id(rank, id) || cpic_b200_comm_init(sim, id) || cpic_b200_pre_step(sim) || cpic_b200_sync(sim))
+	{
+		fprintf(stderr, "rank %d: communicator or pre-step failed\n%s\n", rank, cpic_b200_last_error());
+		return 1;
+	}
+	if(rank == 0)
+	{
+		if(run.output_enabled) fprintf(stderr, "output of several ranks is not written (the reference's ranks overwrite one file, src/output.c:517)\n");
+		fprintf(stderr, "Using %d GPU ranks\n", nranks);
+		printf("%e init-time\n", now() - t0);
+		printf("Simulation runs now\n");
+	}
+	double mean = 0.0, m2 = 0.0;
+	long n = 0;
+	/* the sampling decision is rank 0's (MPI_Bcast(&sim->running), src/sim.c:578); without a broadcast every
+	 * rank runs all the cycles when sampling is on */
+	while(cpic_b200_iter(sim) < run.cycles)
+	{
+		const double t1 = now();
+		if(cpic_b200_step(sim) || cpic_b200_sync(sim))
+		{
+			fprintf(stderr, "rank %d: sim_step failed\n%s\n", rank, cpic_b200_last_error());
+			return 1;
+		}
+		const double t = now() - t1;
+		if(rank == 0 && run.stop_SEM > 0.0)
+		{
+			const double mean0 = mean;
+			const double std = n >= 2 ? sqrt(m2 / (double) (n - 1)) : 0.0;
+			const double sem = n >= 2 ? std / sqrt((double) n) : 0.0;
+			const double rsem = mean0 != 0.0 ? sem / mean0 : sem;
+			n++;
+			mean = mean0 + (t - mean0) / (double) n;
+			m2 += (t - mean0) * (t - mean);
+			printf("stats iter=%ld last=%e mean=%e std=%e sem=%e rsem=%e mem=%ld solver=%e\n",
+					(long) cpic_b200_iter(sim) - 1, t, mean0, std, sem, rsem, 0L, 0.0);
+		}
+	}
+	double ke = 0.0, pe = 0.0;
+	if(!cpic_b200_energy(sim, &ke, &pe)) printf("rank %d: kinetic %.17g potential %.17g\n", rank, ke, pe);
+	if(rank == 0) printf("Simulation ends\n");
+	cpic_b200_destroy(sim);
+	return 0;
+}
+
 /* main of cpic (reference src/cpic.c:50-191) + sim_run (src/sim.c:621-654) */
 extern "C" int
 cpic_b200_main(int argc, char **argv)
@@ -263,6 +362,13 @@ cpic_b200_main(int argc, char **argv)
 	cpic_b200_run_t run;
 	cpic_b200_conf_t *conf = NULL;
 	cpic_b200_params_t p;
+	/* `mpirun -n P cpic <conf>` (src/cpic.c:82-96: one MPI process per Y slab) is P processes of this driver, one
+	 * per GPU, told their place by the environment a launcher sets (CPIC_B200_RANK / CPIC_B200_NRANKS, else
+	 * torchrun's or Open MPI's variables); the 128-byte communicator id travels through a file */
+	const int rank = env_int("CPIC_B200_RANK", env_int("RANK", env_int("OMPI_COMM_WORLD_RANK", 0)));
+	const int nranks = env_int("CPIC_B200_NRANKS", env_int("WORLD_SIZE", env_int("OMPI_COMM_WORLD_SIZE", 1)));
+	const int device = nranks > 1 ? env_int("CPIC_B200_DEVICE", env_int("LOCAL_RANK", env_int("OMPI_COMM_WORLD_LOCAL_RANK", rank))) : -1;
+	if(nranks > 1) return run_ranks(fn, rank, nranks, device, t0);
 	if(cpic_b200_conf_load(fn, &conf) || cpic_b200_conf_params(conf, 0, 1, -1, &p, &run))
 	{
 		fprintf(stderr, "Configuration read failed:\n%s\n", cpic_b200_last_error());

@@ -68,3 +68,32 @@ def test_two_ranks_capacity_growth():
         pytest.skip("needs 2 GPUs")
     out = run_ranks(2, "uniform-small.conf", 40, "fused", port=29615, env={"MGPU_TIGHT": "1"})
     assert "MGPU-CAPS" in out
+
+
+def test_own_driver_on_two_ranks(tmp_path):
+    """`mpirun -n 2 cpic <conf>` as two processes of cpic_b200_cli, one per GPU (rank and communicator id through
+    the environment and a file): the energies of the two slabs add up to those of the single-rank run."""
+    import re
+    if ngpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    cli = os.path.join(ROOT, "cpic_b200", "cpic_b200_cli")
+    text = open(conf_path("2d-2species-small.conf")).read()
+    text = re.sub(r"cycles\s*=\s*\d+", "cycles = 8", text)
+    conf = tmp_path / "run.conf"
+    conf.write_text(text)
+    base = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    procs = [subprocess.Popen([cli, "-q", str(conf)], cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                              env=dict(base, CPIC_B200_RANK=str(r), CPIC_B200_NRANKS="2", CPIC_B200_DEVICE=str(r),
+                                       CPIC_B200_ID_FILE=str(tmp_path / "id"))) for r in range(2)]
+    outs = [p.communicate(timeout=600) for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(o[1][-1500:] for o in outs)
+    assert "Simulation ends" in outs[0][0]
+    energy = lambda t: [(float(a), float(b)) for a, b in re.findall(r"kinetic (\S+) potential (\S+)", t)][0]
+    ke = sum(energy(o[0])[0] for o in outs)
+    pe = sum(energy(o[0])[1] for o in outs)
+    from cpic_b200 import Sim
+    s = Sim.from_conf(str(conf))
+    s.run(8)
+    ke1, pe1 = s.energy()
+    s.close()
+    assert abs(ke - ke1) <= 1e-11 * abs(ke1) and abs(pe - pe1) <= 1e-9 * max(abs(pe1), 1e-300), (ke, ke1, pe, pe1)

@@ -88,3 +88,45 @@ def test_bench_script_on_two_ranks_on_cpu(simt_build):
     assert d["n_gpus"] == 2 and d["multi_rank_check"]["ok"] and d["multi_rank_check"]["worst"] <= 1e-12
     assert d["multi_rank_check"]["count_conserved"] and d["multi_rank_check"]["particles_on_another_rank_than_at_start"] > 0
     assert outs[1][0].strip() == ""          # rank 0 alone prints
+
+
+def _run_driver(lib, conf, rank=None, nranks=1, extra_env=None):
+    code = ("import ctypes as C, sys; L = C.CDLL(sys.argv[1]); "
+            "argv = (C.c_char_p * 3)(b'cpic', b'-q', sys.argv[2].encode()); sys.exit(L.cpic_b200_main(3, argv))")
+    env = dict(os.environ, CPIC_B200_SIMT_CHECK="1", CPIC_B200_NCCL=os.path.join(SIMT, "_build", "libfake_nccl.so"), **(extra_env or {}))
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
+    if rank is not None:
+        env.update(CPIC_B200_RANK=str(rank), CPIC_B200_NRANKS=str(nranks), CPIC_B200_DEVICE="0")
+    return subprocess.Popen([sys.executable, "-c", code, lib, conf], cwd=ROOT, env=env, stdout=subprocess.PIPE,
+                            stderr=subprocess.PIPE, text=True)
+
+
+def test_own_driver_on_two_ranks_on_cpu(simt_build, tmp_path):
+    """`mpirun -n 2 cpic <conf>` as two processes of cpic_b200_main (one per GPU; here the interpreter): the
+    reference's initial conditions drawn per slab, the communicator id through a file, and at the end the
+    energies of the two slabs add up to those of the single-rank run."""
+    import re
+    text = open(conf_path("2d-2species-small.conf")).read()
+    text = re.sub(r"cycles\s*=\s*\d+", "cycles = 6", text)
+    conf = tmp_path / "run.conf"
+    conf.write_text(text)
+    one = _run_driver(simt_build, str(conf))
+    out1, err1 = one.communicate(timeout=600)
+    assert one.returncode == 0, err1[-2000:]
+    idf = str(tmp_path / "id")
+    procs = [_run_driver(simt_build, str(conf), r, 2, {"CPIC_B200_ID_FILE": idf}) for r in range(2)]
+    outs = [p.communicate(timeout=900) for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(o[1][-1500:] for o in outs)
+    assert "Simulation ends" in outs[0][0] and "Simulation ends" not in outs[1][0]
+    energy = lambda text: [(float(a), float(b)) for a, b in re.findall(r"kinetic (\S+) potential (\S+)", text)]
+    ke = sum(energy(o[0])[0][0] for o in outs)
+    pe = sum(energy(o[0])[0][1] for o in outs)
+    # the single-rank driver prints no energies: take them from the library
+    ref = subprocess.run([sys.executable, "-c",
+                          "import sys; sys.path.insert(0, %r); from cpic_b200 import Sim; s = Sim.from_conf(sys.argv[1]); s.run(6); print(*s.energy())" % ROOT,
+                          str(conf)], cwd=ROOT, capture_output=True, text=True, timeout=600,
+                         env=dict(os.environ, CPIC_B200_LIB=simt_build, CPIC_B200_SIMT_CHECK="1"))
+    assert ref.returncode == 0, ref.stderr[-1500:]
+    ke1, pe1 = (float(v) for v in ref.stdout.split()[-2:])
+    assert abs(ke - ke1) <= 1e-11 * abs(ke1) and abs(pe - pe1) <= 1e-9 * max(abs(pe1), 1e-300), (ke, ke1, pe, pe1)
