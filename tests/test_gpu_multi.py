@@ -21,7 +21,7 @@ def ngpus():
 def run_ranks(n, conf, steps, mode="fused", port=29611, env=None):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
            "--master-addr", "127.0.0.1", "--master-port", str(port),
-           os.path.join(ROOT, "tests", "mgpu_worker.py"), conf_path(conf), str(steps), mode]
+           os.path.join(ROOT, "tests", "mgpu_worker.py"), conf if conf.startswith("random:") else conf_path(conf), str(steps), mode]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, **(env or {})))
     assert r.returncode == 0 and "MGPU-OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
     return r.stdout
@@ -97,3 +97,11 @@ def test_own_driver_on_two_ranks(tmp_path):
     ke1, pe1 = s.energy()
     s.close()
     assert abs(ke - ke1) <= 1e-11 * abs(ke1) and abs(pe - pe1) <= 1e-9 * max(abs(pe1), 1e-300), (ke, ke1, pe, pe1)
+
+
+@pytest.mark.parametrize("seed", [1, 3, 4, 7])
+def test_two_ranks_random_configurations(seed):
+    """Random configurations (tests/test_gpu_zz_robustness.py::_random_case) on two ranks against the oracle."""
+    if ngpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    run_ranks(2, f"random:{seed}", 8, "fused", port=29621 + seed)

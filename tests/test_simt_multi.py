@@ -21,7 +21,7 @@ def free_port():
         return s.getsockname()[1]
 
 
-def run_ranks_cpu(lib, n, conf, steps, mode="fused", env=None, timeout=600):
+def run_ranks_cpu(lib, n, conf, steps, mode="fused", env=None, timeout=600, raw=False):
     base = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(free_port()), WORLD_SIZE=str(n),
                 MGPU_DEVICE="cpu", CPIC_B200_LIB=lib, CPIC_B200_SIMT_CHECK="1",
                 CPIC_B200_NCCL=os.path.join(SIMT, "_build", "libfake_nccl.so"), **(env or {}))
@@ -29,7 +29,7 @@ def run_ranks_cpu(lib, n, conf, steps, mode="fused", env=None, timeout=600):
     for r in range(n):
         e = dict(base, RANK=str(r), LOCAL_RANK=str(r))
         procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "mgpu_worker.py"),
-                                       conf_path(conf), str(steps), mode], env=e, cwd=ROOT,
+                                       conf if raw else conf_path(conf), str(steps), mode], env=e, cwd=ROOT,
                                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     outs = []
     try:
@@ -130,3 +130,10 @@ def test_own_driver_on_two_ranks_on_cpu(simt_build, tmp_path):
     assert ref.returncode == 0, ref.stderr[-1500:]
     ke1, pe1 = (float(v) for v in ref.stdout.split()[-2:])
     assert abs(ke - ke1) <= 1e-11 * abs(ke1) and abs(pe - pe1) <= 1e-9 * max(abs(pe1), 1e-300), (ke, ke1, pe, pe1)
+
+
+@pytest.mark.parametrize("ranks,seed", [(2, 1), (2, 3), (2, 4), (4, 7)])
+def test_random_configurations_on_several_ranks_on_cpu(simt_build, ranks, seed):
+    """Random configurations (grid, block size, species, fields, velocities up to a block per step: tests/
+    test_gpu_zz_robustness.py::_random_case) on 2 and 4 ranks against the single-rank oracle."""
+    run_ranks_cpu(simt_build, ranks, f"random:{seed}", 6, raw=True)
