@@ -18,6 +18,7 @@
 
 #include <cufft.h>
 #include <dlfcn.h>
+#include <unistd.h>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -409,13 +410,19 @@ p2p_setup(Comm *c, cudaStream_t stream)
 		cudaIpcMemHandle_t h;
 		if(cudaIpcGetMemHandle(&h, probe) != cudaSuccess) { fail = 1; cudaGetLastError(); }
 	}
-	/* one rank that cannot export (no IPC: different boxes, a container without it, the CPU test
-	 * interpreter) sends everybody down the NCCL path */
-	CCK(cudaMemcpyAsync(probe, &fail, sizeof(int), cudaMemcpyHostToDevice, stream));
-	if(comm_allreduce_max(c, probe, 1, stream)) return 2;
-	CCK(cudaMemcpyAsync(&fail, probe, sizeof(int), cudaMemcpyDeviceToHost, stream));
+	/* one rank that cannot export (no IPC: a container without it, the CPU test interpreter), or ranks on
+	 * different boxes (the host names differ: max(h) != -max(-h)), send everybody down the NCCL path */
+	char host[256] = "";
+	gethostname(host, sizeof(host) - 1);
+	unsigned hh = 2166136261u;
+	for(const char *q = host; *q; q++) hh = (hh ^ (unsigned char) *q) * 16777619u;
+	int v[3] = { fail, (int) (hh & 0x3fffffff), -(int) (hh & 0x3fffffff) };
+	CCK(cudaMemcpyAsync(probe, v, sizeof(v), cudaMemcpyHostToDevice, stream));
+	if(comm_allreduce_max(c, probe, 3, stream)) return 2;
+	CCK(cudaMemcpyAsync(v, probe, sizeof(v), cudaMemcpyDeviceToHost, stream));
 	CCK(cudaStreamSynchronize(stream));
 	cudaFree(probe);
+	fail = v[0] || v[1] != -v[2];
 	c->p2p = !fail;
 	if(!c->p2p) return 0;
 	c->table = (ExportEntry *) calloc((size_t) c->n * X_COUNT, sizeof(ExportEntry));
