@@ -289,7 +289,10 @@ int cpic_b200_write_fields(cpic_b200_sim_t *sim, const char *path, int64_t iter,
 int cpic_b200_write_fields_async(cpic_b200_sim_t *sim, const char *path, int64_t iter, int64_t alignment,
 		int64_t slices, int64_t nx, int64_t ny, double dx, double dy);
 int cpic_b200_output_wait(cpic_b200_sim_t *sim);
-/* The reference's command line, `cpic [-q] <conf>` (src/cpic.c:50-191), on one GPU */
+/* The reference's command line, `cpic [-q] <conf>` (src/cpic.c:50-191). `mpirun -n P cpic <conf>` is P
+ * processes of it, one per GPU: rank, number of ranks and device from CPIC_B200_RANK / CPIC_B200_NRANKS /
+ * CPIC_B200_DEVICE (or torchrun's RANK / WORLD_SIZE / LOCAL_RANK, or Open MPI's OMPI_COMM_WORLD_*), the
+ * communicator id through the file CPIC_B200_ID_FILE */
 int cpic_b200_main(int argc, char **argv);
 
 #ifdef __cplusplus
