@@ -363,3 +363,33 @@ def _blk(n):
 def b_rows(sim, bands, j):
     nby = sim.params.ny // _blk(sim.params.ny)
     return nby * j // bands
+
+
+def test_particles_in_host_order():
+    """cpic_b200_set_host_order / cpic_b200_get_particles_ordered (the drop-in's list refresh): entry k of every
+    array belongs to the k-th id of the host's order, whatever the particle blocks did to the order on the
+    device; an id that the order does not know is an error, as is a wrong count."""
+    import ctypes as C
+    path = conf_path("2d-2species-small.conf")
+    s = Sim.from_conf(path)
+    s.run(5)
+    L = s.L
+    rng = np.random.default_rng(7)
+    for i in range(s.nspecies):
+        ref = s.particles(i)                      # sorted by id
+        n = len(ref["id"])
+        order = rng.permutation(ref["id"]).astype(np.int64)
+        assert L.cpic_b200_set_host_order(s.h, i, n, order.ctypes.data_as(C.c_void_p)) == 0
+        out = {k: np.empty(n) for k in ("x", "y", "ux", "uy", "uz", "Ex", "Ey")}
+        rc = L.cpic_b200_get_particles_ordered(s.h, i, n, *[out[k].ctypes.data_as(C.c_void_p) for k in ("x", "y", "ux", "uy", "uz", "Ex", "Ey")])
+        assert rc == 0, L.cpic_b200_last_error()
+        pos = np.searchsorted(ref["id"], order)
+        for k in ("x", "y", "ux", "uy", "uz"):
+            assert np.array_equal(out[k], ref[k][pos]), (i, k)
+        # wrong count
+        assert L.cpic_b200_get_particles_ordered(s.h, i, n - 1, *[None] * 7) != 0
+        # an order that misses a particle
+        short = order[:-1].copy()
+        assert L.cpic_b200_set_host_order(s.h, i, n - 1, short.ctypes.data_as(C.c_void_p)) == 0
+        assert L.cpic_b200_get_particles_ordered(s.h, i, n - 1, *[out[k].ctypes.data_as(C.c_void_p) for k in ("x", "y", "ux", "uy", "uz", "Ex", "Ey")]) != 0
+    s.close()

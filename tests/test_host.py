@@ -155,3 +155,13 @@ def test_glibc_rand_recurrence_and_jump_ahead(tmp_path):
     assert r.returncode == 0, r.stderr[-2000:]
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "bad=0" in r.stdout, r.stdout[-500:]
+
+
+def test_reference_arm_leaves_other_ranks_silent():
+    """`bench.py --impl reference` under torchrun: rank 0 alone runs and prints; the other ranks exit 0 without work."""
+    import subprocess
+    import sys
+    env = dict(os.environ, RANK="3", WORLD_SIZE="8", LOCAL_RANK="3", BENCH_TINY="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "8"], cwd=ROOT, env=env,
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip() == ""
