@@ -73,3 +73,33 @@ def test_config_B_cyclotron_2048_first_steps():
         g.sync()
         assert_close(field_errors(g, o), what=f"config B fields, iteration {it}")
         assert_close(particle_errors(g, o, params), what=f"config B particles, iteration {it}")
+
+
+def test_config_D_size_independent_properties():
+    """BASELINE.json configs[4] at its full single-GPU size (2048^2 cells, 2.5e8 particles: bench.py's default
+    workload, device initialiser): what must hold at any size -- comm_plasma loses nobody, every particle
+    deposits exactly -q/e0 (CIC weights sum to one), the solve leaves phi with zero mean, the energies stay
+    finite and the kinetic energy of this weakly coupled beam drifts little."""
+    import bench
+    from cpic_b200 import Sim
+    w = bench.WORKLOADS["D"]
+    conf = bench.scaled_conf(conf_path(w["conf"]), w, w["nps"])
+    params, run = load_conf(conf)
+    params.outbox_fraction = 0.19
+    g = Sim(params)
+    n = w["nps"]
+    for i in range(2):
+        g.init_beam(i, n, id0=0, drift=w["drift"][i], spread=w["spread"][i], seed=138 + i)
+    g.pre_step()
+    ke0, _ = g.energy()
+    g.run(20)
+    assert [g.num_particles(i) for i in range(2)] == [n, n]
+    rho = g.field("rho")
+    each = sum(abs(q) / params.e0 * n for q in params.q)
+    expect = sum(-q / params.e0 * n for q in params.q)
+    assert abs(rho.sum() - expect) <= 1e-10 * each
+    phi = g.field("phi")
+    assert abs(phi.mean()) <= 1e-12 * np.abs(phi).max()
+    ke1, pe1 = g.energy()
+    assert np.isfinite(ke1) and np.isfinite(pe1) and abs(ke1 - ke0) / ke0 < 1e-3
+    g.close()
